@@ -1,0 +1,151 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
+
+The reference (pure Python, `omniloc.py`, `utils.py`) is imported from /root/reference behind three
+import-only stub modules (`torch_scatter`, `matplotlib.pyplot`, `open3d` are imported by the
+reference but never used on this path — SURVEY.md §8c).  Every fixture stores its INPUTS (uint8
+colours/panorama, float32 xyz, poses) and the reference's OUTPUTS, so the tests never need the
+reference or the synthetic generator to be bit-reproducible on another machine.
+"""
+import os
+import sys
+import types
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("PICCOLO_REFERENCE", "/root/reference")
+
+
+def import_reference():
+    ts = types.ModuleType("torch_scatter"); ts.scatter_min = None
+    mpl = types.ModuleType("matplotlib"); plt = types.ModuleType("matplotlib.pyplot"); mpl.pyplot = plt
+    o3d = types.ModuleType("open3d")
+    sys.modules.setdefault("torch_scatter", ts)
+    sys.modules.setdefault("matplotlib", mpl)
+    sys.modules.setdefault("matplotlib.pyplot", plt)
+    sys.modules.setdefault("open3d", o3d)
+    sys.path.insert(0, REF)
+    import omniloc as ref_omniloc
+    import utils as ref_utils
+    return ref_omniloc, ref_utils
+
+
+def ref_loss_grad(ref_omniloc, xyz, rgb, img, pose, dtype):
+    cfg = namedtuple("C", ["num_input"])(1)
+    xyz_t, rgb_t, img_t = [torch.from_numpy(a).to(dtype) for a in (xyz, rgb, img)]
+    mod = ref_omniloc.SamplingLoss(xyz_t, rgb_t, img_t, torch.device("cpu"), cfg)
+    mod.tensor_0 = mod.tensor_0.to(dtype); mod.tensor_1 = mod.tensor_1.to(dtype)
+    p = torch.tensor(pose, dtype=dtype)
+    t = p[:3].reshape(3, 1).clone().requires_grad_()
+    yaw, pitch, roll = [p[i:i + 1].clone().requires_grad_() for i in (3, 4, 5)]
+    loss = mod(t, yaw, pitch, roll)
+    if torch.isnan(loss):
+        return float("nan"), np.full(6, np.nan)
+    loss.backward()
+    g = np.concatenate([t.grad.reshape(3).numpy(), yaw.grad.numpy(), pitch.grad.numpy(), roll.grad.numpy()])
+    return float(loss), g.astype(np.float64)
+
+
+def main():
+    from piccolo_b200 import synth
+    ref_omniloc, ref_utils = import_reference()
+    torch.manual_seed(2)
+    torch.set_num_threads(8)
+    Cfg = namedtuple("Cfg", ["num_input", "lr", "num_iter", "patience", "factor", "out_of_room_quantile"])
+
+    # ---------------- fixture 1: loss + gradient, small scene with edge cases -----------------
+    sc = synth.make_scene(4096, 64, 128, seed=2)
+    rng = np.random.default_rng(11)
+    poses = []
+    gt = sc.gt_pose
+    poses.append(gt)
+    for _ in range(9):
+        p = gt + np.concatenate([rng.normal(0, 0.3, 3), rng.normal(0, 0.25, 3)])
+        poses.append(p)
+    for _ in range(4):   # arbitrary poses anywhere in the room, any orientation
+        p = np.concatenate([np.asarray(sc.room) * (0.15 + 0.7 * rng.random(3)), rng.random(3) * 2 * np.pi])
+        poses.append(p)
+    xyz = sc.xyz.copy()
+    poses.append(np.concatenate([xyz[17].astype(np.float64), [0.3, 0.0, 0.0]]))           # camera exactly on a point
+    poses.append(np.array([4.0, 3.0, 2.95, 1.0, 0.0, 0.0]))                               # near the ceiling: many v at the clip
+    poses = np.asarray(poses, dtype=np.float32)
+    rgb, img = sc.rgb, sc.img
+    out = {"xyz": xyz, "rgb8": sc.rgb8, "img8": sc.img8, "poses": poses}
+    l32, g32, l64, g64 = [], [], [], []
+    for p in poses:
+        a, b = ref_loss_grad(ref_omniloc, xyz, rgb, img, p, torch.float32); l32.append(a); g32.append(b)
+        a, b = ref_loss_grad(ref_omniloc, xyz, rgb, img, p.astype(np.float64), torch.float64); l64.append(a); g64.append(b)
+    out.update(loss32=np.array(l32), grad32=np.array(g32), loss64=np.array(l64), grad64=np.array(g64))
+    # batched module on the first 4 poses
+    cfgb = Cfg(4, 0.1, 100, 5, 0.9, 0.05)
+    bmod = ref_omniloc.BatchSamplingLoss(torch.from_numpy(xyz), torch.from_numpy(rgb), torch.from_numpy(img), torch.device("cpu"), cfgb)
+    pb = torch.from_numpy(poses[:4])
+    tot, lst = bmod(pb[:, :3].unsqueeze(-1), pb[:, 3:4], pb[:, 4:5], pb[:, 5:6])
+    out.update(batch_total=np.float32(tot.item()), batch_list=lst.numpy())
+    # all-black panorama -> NaN
+    a, _ = ref_loss_grad(ref_omniloc, xyz, rgb, np.zeros_like(img), poses[0], torch.float32)
+    out.update(black_loss=np.float32(a))
+    # quantile box
+    qs = [ref_utils.quantile(torch.from_numpy(xyz[:, k]), 0.05) for k in range(3)]
+    out.update(box_lo=np.array([float(q[0]) for q in qs], dtype=np.float32), box_hi=np.array([float(q[1]) for q in qs], dtype=np.float32))
+    np.savez_compressed(os.path.join(HERE, "loss_small.npz"), **out)
+    print("loss_small: loss32", out["loss32"][:4], "max|g32-g64|", np.nanmax(np.abs(out["grad32"] - out["grad64"])))
+
+    # ---------------- fixture 2: grid scoring / top-K (trim_input_loss) ------------------------
+    grid = synth.pose_grid(sc.room, (3, 3, 2), 8)
+    trans = torch.from_numpy(np.ascontiguousarray(grid[::8, :3]))
+    rot = torch.from_numpy(np.ascontiguousarray(grid[:8, 3:]))
+    xyz_t, rgb_t, img_t = torch.from_numpy(xyz), torch.from_numpy(rgb), torch.from_numpy(img)
+    tt_all, rr_all = ref_utils.trim_input_loss(img_t, xyz_t, rgb_t, trans, rot, len(trans) * len(rot))
+    tt, rr = ref_utils.trim_input_loss(img_t, xyz_t, rgb_t, trans, rot, 10)
+    table = np.array([ref_loss_grad(ref_omniloc, xyz, rgb, img, g, torch.float32)[0] for g in grid])
+    np.savez_compressed(os.path.join(HERE, "score_small.npz"), trans=trans.numpy(), rot=rot.numpy(), grid=grid,
+                        loss_table=table, top10_trans=tt.numpy(), top10_rot=rr.numpy(),
+                        all_trans=tt_all.numpy(), all_rot=rr_all.numpy())
+    print("score_small: best", table.min(), "worst", table.max())
+
+    # ---------------- fixture 3: refinement trajectories (omniloc / omniloc_batch) -------------
+    def run_refine(scn, starts, num_iter, tag, factor):
+        xyz_t, rgb_t, img_t = torch.from_numpy(scn.xyz), torch.from_numpy(scn.rgb), torch.from_numpy(scn.img)
+        st = torch.from_numpy(starts)
+        cfg = Cfg(len(starts), 0.1, num_iter, 5, factor, 0.05)
+        seq = [ref_omniloc.omniloc(img_t, xyz_t, rgb_t, st[:, :3].clone(), st[:, 3:].clone(), i, cfg, None) for i in range(len(starts))]
+        bat = ref_omniloc.omniloc_batch(img_t, xyz_t, rgb_t, st[:, :3].clone(), st[:, 3:].clone(), cfg, None)
+        res = {"xyz": scn.xyz, "rgb8": scn.rgb8, "img8": scn.img8, "starts": starts, "gt_pose": scn.gt_pose,
+               "num_iter": num_iter, "factor": factor,
+               "seq_t": np.stack([s[0].detach().numpy().reshape(3) for s in seq]),
+               "seq_R": np.stack([s[1].detach().numpy() for s in seq]),
+               "seq_loss": np.array([float(s[2]) for s in seq], dtype=np.float32),
+               "bat_t": bat[0].detach().numpy().reshape(3), "bat_R": bat[1].detach().numpy(), "bat_loss": np.float32(float(bat[2]))}
+        np.savez_compressed(os.path.join(HERE, tag + ".npz"), **res)
+        print(tag, "seq_loss", res["seq_loss"], "bat_loss", res["bat_loss"], "t", res["bat_t"], "gt", scn.gt_pose[:3])
+
+    rng = np.random.default_rng(5)
+    starts = np.stack([gt + np.concatenate([rng.normal(0, 0.25, 3), rng.normal(0, 0.15, 3)]) for _ in range(3)]).astype(np.float32)
+    starts[2, :3] = [7.9, 0.2, 2.9]   # starts outside the 5-95 % box: exercises the clamp (and the batch quirk)
+    run_refine(sc, starts, 30, "refine_small", 0.8)
+
+    sc2 = synth.make_scene(50000, 256, 512, seed=3)
+    rng = np.random.default_rng(6)
+    starts2 = np.stack([sc2.gt_pose + np.concatenate([rng.normal(0, 0.2, 3), rng.normal(0, 0.12, 3)]) for _ in range(3)]).astype(np.float32)
+    run_refine(sc2, starts2, 100, "refine_medium", 0.8)
+
+    # medium loss/grad vectors
+    poses2 = np.concatenate([starts2, sc2.gt_pose[None].astype(np.float32)], axis=0)
+    l32 = []; g32 = []; l64 = []; g64 = []
+    for p in poses2:
+        a, b = ref_loss_grad(ref_omniloc, sc2.xyz, sc2.rgb, sc2.img, p, torch.float32); l32.append(a); g32.append(b)
+        a, b = ref_loss_grad(ref_omniloc, sc2.xyz, sc2.rgb, sc2.img, p.astype(np.float64), torch.float64); l64.append(a); g64.append(b)
+    np.savez_compressed(os.path.join(HERE, "loss_medium.npz"), poses=poses2, loss32=np.array(l32), grad32=np.array(g32),
+                        loss64=np.array(l64), grad64=np.array(g64))
+    print("loss_medium", l32)
+
+
+if __name__ == "__main__":
+    main()
