@@ -1,0 +1,116 @@
+/* piccolo_b200 — C ABI of the B200-native PICCOLO sampling-loss pose search.
+ *
+ * Drop-in boundary.  The reference (82magnolia/piccolo) is pure Python and has no FFI; its hot
+ * path is the torch op chain behind these call sites, which the entry points below replace:
+ *
+ *   pcl_cloud_create   the per-room upload `xyz.to(device)`, `rgb.to(device)`  (localize.py:159-164)
+ *                      + the clamp box `quantile()`                             (utils.py:208-229,
+ *                        omniloc.py:53-55, :245-247)
+ *   pcl_image_create   the per-query upload `img.to(device)`                    (localize.py:169-170, :212-213)
+ *   pcl_score          the T×R forward-only loop of `trim_input_loss`           (utils.py:484-499)
+ *                      and `sampling_loss`                                      (omniloc.py:105-157)
+ *   pcl_topk           `loss_table.flatten().argsort()[:num_input]`             (utils.py:501-502)
+ *   pcl_loss_fwd_bwd   `SamplingLoss.forward` + autograd backward               (omniloc.py:171-202)
+ *                      `BatchSamplingLoss.forward` + backward                   (omniloc.py:311-356)
+ *   pcl_refine_*       the optimisation loops of `omniloc` / `omniloc_batch`:
+ *                      loss, backward, Adam.step, ReduceLROnPlateau.step, clamp (omniloc.py:44-58, :249-269)
+ *
+ * Conventions
+ *   - every pointer named *_dev is a CUDA device pointer on the current device; everything else is
+ *     host memory.  All tensors are float32, contiguous, row-major.
+ *   - a pose is 6 floats (tx, ty, tz, yaw, pitch, roll); R = Rz(yaw)·Ry(pitch)·Rx(roll)
+ *     (utils.py:425-453), camera-frame point q = R (p - t).
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls are asynchronous with
+ *     respect to the host unless stated otherwise; results are ordered on `stream`.
+ *   - every function returns 0 on success or a negative pcl_status; pcl_last_error() returns a
+ *     thread-local message for the last failure.  No C++ exception crosses the ABI.
+ *   - handles (pcl_cloud, pcl_image) are immutable after creation and may be shared by streams;
+ *     a pcl_refine is single-owner.  The library never frees caller memory.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     PCL_ERR_CUDA.
+ */
+#ifndef PICCOLO_B200_H
+#define PICCOLO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCL_ABI_VERSION 1
+
+typedef enum pcl_status {
+  PCL_OK = 0,
+  PCL_ERR_INVALID = -1,   /* bad argument */
+  PCL_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+  PCL_ERR_FORMAT = -3     /* image cannot be represented in the requested texel format */
+} pcl_status;
+
+/* texel formats of a pcl_image */
+#define PCL_IMAGE_AUTO 0   /* u8 quad table if every value is k/255 exactly, else f32 */
+#define PCL_IMAGE_U8Q 1    /* 16-byte footprint entries {nw,ne,sw,se} RGBA8: one 128-bit load per sample */
+#define PCL_IMAGE_F32 2    /* fp32 RGBA texels: arbitrary float images */
+#define PCL_IMAGE_U8P 3    /* plain RGBA8 texels (4 B/texel): smallest table, four 32-bit loads */
+
+/* point ordering of a pcl_cloud */
+#define PCL_CLOUD_KEEP_ORDER 0
+#define PCL_CLOUD_MORTON 1   /* sort by 3-D Morton code: neighbouring lanes gather neighbouring texels */
+
+typedef struct pcl_cloud pcl_cloud;
+typedef struct pcl_image pcl_image;
+typedef struct pcl_refine pcl_refine;
+
+int pcl_abi_version(void);
+const char* pcl_last_error(void);
+/* number of kernels launched by this library in the calling process (all threads) since load */
+int64_t pcl_launch_count(void);
+
+/* ---- coloured point cloud ------------------------------------------------------------------ */
+/* xyz_n3_dev, rgb_n3_dev: (N,3) float32.  q: out_of_room_quantile (clamp box = order statistics
+ * int(N*q) and int(N*(1-q)) per axis, utils.py:222-227).  Synchronises `stream` before returning. */
+int pcl_cloud_create(const float* xyz_n3_dev, const float* rgb_n3_dev, int64_t n, double q, int order,
+                     void* stream, pcl_cloud** out);
+int64_t pcl_cloud_size(const pcl_cloud* c);
+/* lo_hi[6] = {x_min, y_min, z_min, x_max, y_max, z_max} (host) */
+int pcl_cloud_bounds(const pcl_cloud* c, float* lo_hi);
+void pcl_cloud_destroy(pcl_cloud* c);
+
+/* ---- equirectangular panorama -------------------------------------------------------------- */
+/* img_hw3_dev: (H,W,3) float32 in [0,1].  Synchronises `stream` before returning. */
+int pcl_image_create(const float* img_hw3_dev, int h, int w, int format, void* stream, pcl_image** out);
+int pcl_image_format(const pcl_image* im);
+void pcl_image_destroy(pcl_image* im);
+
+/* ---- forward-only scoring of P poses ------------------------------------------------------- */
+/* loss_p_dev[p] = Σ m·e / Σ m (NaN when no point survives the zero mask); count_p_dev (nullable) = Σ m */
+int pcl_score(const pcl_cloud* c, const pcl_image* im, const float* poses_p6_dev, int64_t p,
+              float* loss_p_dev, float* count_p_dev, void* stream);
+
+/* indices of the k smallest losses, ascending, ties -> lower index, NaN last */
+int pcl_topk(const float* loss_p_dev, int64_t p, int k, int64_t* idx_k_dev, void* stream);
+
+/* ---- loss + analytic 6-DoF gradient of B poses (autograd.Function backend) ------------------- */
+/* grad_b6_dev[b] = d loss_b / d (tx,ty,tz,yaw,pitch,roll) */
+int pcl_loss_fwd_bwd(const pcl_cloud* c, const pcl_image* im, const float* poses_b6_dev, int b,
+                     float* loss_b_dev, float* count_b_dev, float* grad_b6_dev, void* stream);
+
+/* ---- fused refinement: one launch per iteration for the whole candidate batch ---------------- */
+/* batch_semantics = 0: `omniloc` (forward at the clamped parameter, omniloc.py:44-58)
+ * batch_semantics = 1: `omniloc_batch` (forward at the pre-clamp copy, omniloc.py:260-269) */
+int pcl_refine_create(int b, double lr, double factor, int patience, int batch_semantics, pcl_refine** out);
+/* load B start poses and reset Adam / plateau state */
+int pcl_refine_reset(pcl_refine* r, const float* poses_b6_dev, void* stream);
+/* run num_iter iterations: each is ONE kernel = loss + backward + reduction + Adam + plateau + clamp */
+int pcl_refine_run(pcl_refine* r, const pcl_cloud* c, const pcl_image* im, int num_iter, void* stream);
+/* pose_b6_dev: what the reference returns (clamped parameter, or the un-clamped copy under batch
+ * semantics); param_b6_dev (nullable): Adam's clamped parameter; loss_b_dev: loss of the LAST forward;
+ * lr_b_dev (nullable, double): current learning rates */
+int pcl_refine_read(const pcl_refine* r, float* pose_b6_dev, float* param_b6_dev, float* loss_b_dev,
+                    double* lr_b_dev, void* stream);
+void pcl_refine_destroy(pcl_refine* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PICCOLO_B200_H */

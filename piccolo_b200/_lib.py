@@ -1,0 +1,73 @@
+"""ctypes binding of libpiccolo_b200.so (C ABI declared in include/piccolo_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, an exception is raised.
+Build it with `python -c "import __graft_entry__ as g; g.build()"` or `make -C piccolo_b200/csrc`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpiccolo_b200.so")
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_void_pp = ctypes.POINTER(ctypes.c_void_p)
+
+# name -> (restype, argtypes); mirrors include/piccolo_b200.h one to one
+SIGNATURES = {
+    "pcl_abi_version": (ctypes.c_int, []),
+    "pcl_last_error": (ctypes.c_char_p, []),
+    "pcl_launch_count": (ctypes.c_int64, []),
+    "pcl_cloud_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_int, ctypes.c_void_p, c_void_pp]),
+    "pcl_cloud_size": (ctypes.c_int64, [ctypes.c_void_p]),
+    "pcl_cloud_bounds": (ctypes.c_int, [ctypes.c_void_p, c_float_p]),
+    "pcl_cloud_destroy": (None, [ctypes.c_void_p]),
+    "pcl_image_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, c_void_pp]),
+    "pcl_image_format": (ctypes.c_int, [ctypes.c_void_p]),
+    "pcl_image_destroy": (None, [ctypes.c_void_p]),
+    "pcl_score": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pcl_topk": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "pcl_loss_fwd_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pcl_refine_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, c_void_pp]),
+    "pcl_refine_reset": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pcl_refine_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "pcl_refine_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pcl_refine_destroy": (None, [ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+class PiccoloError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the library once; fail loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PiccoloError(
+            f"{LIB_PATH} not found: the CUDA library is not built. Run `make -C piccolo_b200/csrc` "
+            "(or __graft_entry__.build()). piccolo_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pcl_abi_version() != 1:
+        raise PiccoloError("libpiccolo_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().pcl_last_error()
+        raise PiccoloError(f"piccolo_b200 call failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(load().pcl_launch_count())

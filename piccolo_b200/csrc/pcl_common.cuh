@@ -1,0 +1,90 @@
+// Shared declarations of the piccolo_b200 CUDA library (host side + handle layouts).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/piccolo_b200.h"
+#include "pcl_eval.cuh"
+
+#define PCL_THREADS 256
+#define PCL_WARPS (PCL_THREADS / 32)
+#define PCL_TILE_ALIGN 2048       // clouds are padded to a multiple of this many points
+#define PCL_MAX_POSE_BLOCK 32     // poses a CTA keeps in shared memory
+#define PCL_NSUM 8                // {Σme, Σm, a(3), τ(3)}
+
+void pcl_set_error(const char* fmt, ...);
+extern std::atomic<long long> g_pcl_launches;
+
+#define PCL_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      pcl_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return PCL_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define PCL_LAUNCH_CHECK()                      \
+  do {                                          \
+    g_pcl_launches.fetch_add(1);                \
+    PCL_CUDA(cudaGetLastError());               \
+  } while (0)
+
+struct pcl_cloud {
+  float* block;                 // one allocation: x|y|z|r|g|b, each n_pad floats
+  float *x, *y, *z, *r, *g, *b;
+  int64_t n, n_pad;
+  float lo_hi[6];
+  int order;
+};
+
+struct pcl_image {
+  void* data;
+  size_t bytes;
+  PclImage view;                // view.data == data
+};
+
+// per-candidate optimiser state (device)
+struct PclRefineState {
+  float m[6], v[6];             // Adam moments
+  float param[6];               // Adam's parameter (translation clamped to the box)
+  float last_loss;
+  int step;
+  int bad;
+  int pad;
+  double lr, best;
+};
+
+struct pcl_refine {
+  int B, patience, batch_semantics;
+  double lr0, factor;
+  PclRefineState* state;        // [B]
+  float* evalp;                 // [B][6] pose evaluated by the next forward
+  float* partial;               // grow-only scratch for per-CTA partial sums
+  size_t partial_floats;
+  unsigned int* counters;       // last-block-done tickets
+  float* loss;                  // [B]
+};
+
+struct PclCloudView {
+  const float *x, *y, *z, *r, *g, *b;
+  long long n;
+};
+
+// what the last CTA of a pose block does with the reduced sums
+enum { PCL_FIN_SCORE = 0, PCL_FIN_GRAD = 1, PCL_FIN_REFINE = 2 };
+
+struct PclFinalize {
+  int mode;
+  float* loss;                  // [P]
+  float* count;                 // [P] nullable
+  float* grad;                  // [P][6]           (GRAD)
+  PclRefineState* state;        // [P]              (REFINE)
+  float* evalp;                 // [P][6] in/out    (REFINE)
+  float lo[3], hi[3];           // clamp box        (REFINE)
+  double factor;
+  int patience;
+  int batch_semantics;
+};

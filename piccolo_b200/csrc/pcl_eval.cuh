@@ -1,0 +1,305 @@
+// Per-(pose, point) evaluation of the PICCOLO sampling loss and its analytic camera-frame gradient.
+//
+// One call = one pose·point evaluation:  rigid transform (omniloc.py:190-191) -> equirectangular
+// projection (utils.py:44-59) -> clip ±0.99 + bilinear sample, align_corners=False, zeros padding
+// (utils.py:96-98) -> zero mask + L2 colour residual (omniloc.py:198-200) and, when BWD, the
+// gradient w.r.t. the camera-frame point q, accumulated as force a = Σ g_q and
+// torque τ = Σ q × g_q  (dL/dangle = ω_angle · τ, dL/dt = -Rᵀ a; see pcl_finish_gradient).
+//
+// The header is `__host__ __device__` clean: tests/ compile it for the host (tests/emul) to check
+// the arithmetic against the oracle without a GPU.  The product only ever runs it on the device.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define PCL_HD __host__ __device__ __forceinline__
+#else
+#define PCL_HD inline
+#endif
+
+#define PCL_PI_F 3.14159265358979323846f
+#define PCL_HALF_PI_F 1.57079632679489661923f
+
+// image formats
+enum { PCL_FMT_AUTO = 0, PCL_FMT_U8Q = 1, PCL_FMT_F32 = 2, PCL_FMT_U8P = 3 };
+
+struct PclPose {          // R row-major, then t   (48 bytes, 16-byte aligned for LDS.128)
+  float r00, r01, r02, r10;
+  float r11, r12, r20, r21;
+  float r22, tx, ty, tz;
+};
+
+struct PclImage {
+  const void* data;       // format-dependent texel table (see pcl_image.cu)
+  int H, W;
+  int pitch;              // entries per row of the padded table
+  int fmt;
+  float kx, cx;           // ix = cx - phi * kx      (phi = atan2(qy, qx+1e-6) in (-pi, pi])
+  float ky, cy;           // iy = theta * ky + cy    (theta = atan2(rho, qz+1e-6) in [0, pi])
+  float ix_lo, ix_hi, iy_lo, iy_hi;   // the ±0.99 clip expressed in pixel coordinates
+  float tex_scale;        // multiplies a blended texel to bring it to [0,1] (1/255 for u8 formats)
+};
+
+// Geometry constants of an H×W panorama (host side; fp32 chain of grid_sampler_unnormalize for the
+// clip bounds so that clipped points land on exactly the reference's pixel coordinate).
+inline void pcl_image_set_geometry(PclImage& I, int H, int W) {
+  I.H = H; I.W = W;
+  I.kx = (float)((double)W / (2.0 * 3.14159265358979323846));
+  I.cx = 0.5f * (float)W - 0.5f;
+  I.ky = (float)((double)H / 3.14159265358979323846);
+  I.cy = -0.5f;
+  const float c = 0.99f;
+  I.ix_hi = ((c + 1.0f) * (float)W - 1.0f) / 2.0f;
+  I.ix_lo = ((-c + 1.0f) * (float)W - 1.0f) / 2.0f;
+  I.iy_hi = ((c + 1.0f) * (float)H - 1.0f) / 2.0f;
+  I.iy_lo = ((-c + 1.0f) * (float)H - 1.0f) / 2.0f;
+}
+
+struct PclAcc {           // per-pose running sums
+  float se, sm;           // Σ m·e , Σ m
+  float ax, ay, az;       // Σ g_q            (BWD only)
+  float tx, ty, tz;       // Σ q × g_q        (BWD only)
+};
+
+// ---------------------------------------------------------------------------------------------
+// fast math primitives (device: single MUFU op; host: libm, for the emulation tests)
+// ---------------------------------------------------------------------------------------------
+PCL_HD float pcl_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return 1.0f / x;
+#endif
+}
+PCL_HD float pcl_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+
+// atan(a) for a in [0,1]:  a + a^3 q(a^2), q minimax of degree 6 (max abs error 1.1e-7 in fp32).
+PCL_HD float pcl_atan01(float a) {
+  const float s = a * a;
+  float q = -0.004355400800704956f;
+  q = fmaf(q, s, 0.02304011955857277f);
+  q = fmaf(q, s, -0.057773567736148834f);
+  q = fmaf(q, s, 0.09794232994318008f);
+  q = fmaf(q, s, -0.13976581394672394f);
+  q = fmaf(q, s, 0.19962704181671143f);
+  q = fmaf(q, s, -0.3333165943622589f);
+  return fmaf(a * s, q, a);
+}
+
+// atan2(y, x) in (-pi, pi]
+PCL_HD float pcl_atan2(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(fmaxf(ax, ay), 1e-37f);
+  const float mn = fminf(ax, ay);
+  float r = pcl_atan01(mn * pcl_rcp(mx));
+  r = (ay > ax) ? (PCL_HALF_PI_F - r) : r;
+  r = (x < 0.0f) ? (PCL_PI_F - r) : r;
+  return copysignf(r, y);
+}
+
+// atan2(y, x) for y >= 0, result in [0, pi]
+PCL_HD float pcl_atan2_pos(float y, float x) {
+  const float ax = fabsf(x);
+  const float mx = fmaxf(fmaxf(ax, y), 1e-37f);
+  const float mn = fminf(ax, y);
+  float r = pcl_atan01(mn * pcl_rcp(mx));
+  r = (y > ax) ? (PCL_HALF_PI_F - r) : r;
+  r = (x < 0.0f) ? (PCL_PI_F - r) : r;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// texel fetch: returns the four taps of the footprint whose north-west texel is (x0, y0) with
+// x0 in [-1, W-1], y0 in [-1, H-1]; out-of-image taps read the zero border baked into the table.
+// Values are in "table units" (0..255 for the u8 formats, 0..1 for f32).
+// ---------------------------------------------------------------------------------------------
+struct PclTaps { float nw[3], ne[3], sw[3], se[3]; };
+
+PCL_HD float pcl_u8_to_float(uint32_t w, int byte) {
+#if defined(__CUDA_ARCH__)
+  // place the byte in the low mantissa of 2^23, then subtract 2^23: PRMT + FADD, exact
+  const uint32_t sel = 0x7650u + (uint32_t)byte;
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f;
+#else
+  return (float)((w >> (8 * byte)) & 0xffu);
+#endif
+}
+
+#if defined(__CUDACC__)
+typedef uint4 pcl_u4;
+typedef float4 pcl_f4;
+#else
+struct pcl_u4 { uint32_t x, y, z, w; };
+struct pcl_f4 { float x, y, z, w; };
+#endif
+#if defined(__CUDA_ARCH__)
+#define PCL_LDG128(p) __ldg(reinterpret_cast<const uint4*>(p))
+#define PCL_LDG32(p) __ldg(reinterpret_cast<const uint32_t*>(p))
+#define PCL_LDGF4(p) __ldg(reinterpret_cast<const float4*>(p))
+#else
+#define PCL_LDG128(p) (*reinterpret_cast<const pcl_u4*>(p))
+#define PCL_LDG32(p) (*reinterpret_cast<const uint32_t*>(p))
+#define PCL_LDGF4(p) (*reinterpret_cast<const pcl_f4*>(p))
+#endif
+
+template <int FMT>
+PCL_HD void pcl_fetch(const PclImage& I, int x0, int y0, PclTaps& t) {
+  if (FMT == PCL_FMT_U8Q) {
+    // one 16-byte entry per footprint: {nw, ne, sw, se} as RGBA8
+    const pcl_u4* tab = reinterpret_cast<const pcl_u4*>(I.data);
+    const pcl_u4 e = PCL_LDG128(tab + ((size_t)(y0 + 1) * (size_t)I.pitch + (size_t)(x0 + 1)));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      t.nw[c] = pcl_u8_to_float(e.x, c);
+      t.ne[c] = pcl_u8_to_float(e.y, c);
+      t.sw[c] = pcl_u8_to_float(e.z, c);
+      t.se[c] = pcl_u8_to_float(e.w, c);
+    }
+  } else if (FMT == PCL_FMT_U8P) {
+    // plain RGBA8 texels with a 1-texel zero border: 4 B per texel, four 32-bit loads
+    const uint32_t* tab = reinterpret_cast<const uint32_t*>(I.data);
+    const uint32_t* p = tab + ((size_t)(y0 + 1) * (size_t)I.pitch + (size_t)(x0 + 1));
+    const uint32_t a = PCL_LDG32(p), b = PCL_LDG32(p + 1), c2 = PCL_LDG32(p + I.pitch), d = PCL_LDG32(p + I.pitch + 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      t.nw[c] = pcl_u8_to_float(a, c);
+      t.ne[c] = pcl_u8_to_float(b, c);
+      t.sw[c] = pcl_u8_to_float(c2, c);
+      t.se[c] = pcl_u8_to_float(d, c);
+    }
+  } else {
+    // fp32 RGBA texels with a 1-texel zero border: 16 B per texel, four 128-bit loads
+    const pcl_f4* tab = reinterpret_cast<const pcl_f4*>(I.data);
+    const pcl_f4* p = tab + ((size_t)(y0 + 1) * (size_t)I.pitch + (size_t)(x0 + 1));
+    const pcl_f4 a = PCL_LDGF4(p), b = PCL_LDGF4(p + 1), c2 = PCL_LDGF4(p + I.pitch), d = PCL_LDGF4(p + I.pitch + 1);
+    t.nw[0] = a.x; t.nw[1] = a.y; t.nw[2] = a.z;
+    t.ne[0] = b.x; t.ne[1] = b.y; t.ne[2] = b.z;
+    t.sw[0] = c2.x; t.sw[1] = c2.y; t.sw[2] = c2.z;
+    t.se[0] = d.x; t.se[1] = d.y; t.se[2] = d.z;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// one pose·point evaluation
+// ---------------------------------------------------------------------------------------------
+template <int FMT, bool BWD>
+PCL_HD void pcl_eval(const PclPose& P, const PclImage& I, float px, float py, float pz,
+                     float cr, float cg, float cb, bool valid, PclAcc& acc) {
+  // q = R (p - t)
+  const float dx = px - P.tx, dy = py - P.ty, dz = pz - P.tz;
+  const float qx = fmaf(P.r02, dz, fmaf(P.r01, dy, P.r00 * dx));
+  const float qy = fmaf(P.r12, dz, fmaf(P.r11, dy, P.r10 * dx));
+  const float qz = fmaf(P.r22, dz, fmaf(P.r21, dy, P.r20 * dx));
+  const float xp = qx + 1e-6f, zp = qz + 1e-6f;
+  const float rho2 = fmaf(qx, qx, qy * qy);
+  const float rinv = pcl_rsqrt(fmaxf(rho2, 1e-37f));
+  const float rho = rho2 * rinv;
+
+  const float phi = pcl_atan2(qy, xp);
+  const float theta = pcl_atan2_pos(rho, zp);
+  const float ix_raw = fmaf(-phi, I.kx, I.cx);
+  const float iy_raw = fmaf(theta, I.ky, I.cy);
+  const float ix = fminf(fmaxf(ix_raw, I.ix_lo), I.ix_hi);
+  const float iy = fminf(fmaxf(iy_raw, I.iy_lo), I.iy_hi);
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const float fx = ix - fx0, fy = iy - fy0;
+
+  PclTaps t;
+  pcl_fetch<FMT>(I, (int)fx0, (int)fy0, t);
+
+  float d[3], dsdx[3], dsdy[3], ssum = 0.0f;
+  const float col[3] = {cr, cg, cb};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float dxt = t.ne[c] - t.nw[c];
+    const float dxb = t.se[c] - t.sw[c];
+    const float top = fmaf(fx, dxt, t.nw[c]);
+    const float bot = fmaf(fx, dxb, t.sw[c]);
+    const float dyv = bot - top;
+    const float s = fmaf(fy, dyv, top);
+    ssum += s;
+    d[c] = fmaf(s, I.tex_scale, -col[c]);
+    if (BWD) {
+      dsdx[c] = fmaf(fy, dxb - dxt, dxt);
+      dsdy[c] = dyv;
+    }
+  }
+  const bool m = valid && (ssum > 0.0f);      // texels are >= 0, so Σ == 0  <=>  all three are 0
+  const float e2 = fmaf(d[2], d[2], fmaf(d[1], d[1], d[0] * d[0]));
+  const float einv = pcl_rsqrt(fmaxf(e2, 1e-37f));
+  const float e = e2 * einv;
+  acc.se += m ? e : 0.0f;
+  acc.sm += m ? 1.0f : 0.0f;
+
+  if (BWD) {
+    // g_s = m (s - c)/e ; texel-unit and pixel-unit factors (tex_scale, W/2·(-1/pi), H/2·(2/pi)) are
+    // constants of the pose and are applied once to the reduced sums (pcl_finish_gradient).
+    const float w = m ? einv : 0.0f;
+    float gix = fmaf(d[2], dsdx[2], fmaf(d[1], dsdx[1], d[0] * dsdx[0])) * w;
+    float giy = fmaf(d[2], dsdy[2], fmaf(d[1], dsdy[1], d[0] * dsdy[0])) * w;
+    gix = (ix_raw == ix) ? gix : 0.0f;        // clip passes the gradient inclusively at the bound
+    giy = (iy_raw == iy) ? giy : 0.0f;
+    const float dphi = fmaf(xp, xp, qy * qy);
+    const float dth = fmaf(zp, zp, rho2);
+    const float rr = pcl_rcp(fmaxf(dphi * dth, 1e-37f));
+    // ix = cx - kx·phi, iy = ky·theta + cy   =>   g_phi = -kx·g_ix, g_theta = ky·g_iy
+    // phi = atan2(qy, xp):   dphi/dqx = -qy/dphi, dphi/dqy = xp/dphi
+    // theta = atan2(rho, zp): dtheta/drho = zp/dth, dtheta/dzp = -rho/dth ; drho/dq{x,y} = q{x,y}/rho
+    const float A = (-I.kx * gix) * (rr * dth);         // g_phi / (xp² + qy²)
+    const float B = (I.ky * giy) * (rr * dphi);         // g_theta / (rho² + zp²)
+    const float Bz = B * zp * rinv;                     // rho == 0  ->  multiplied by qx = qy = 0 below
+    const float gqx = fmaf(Bz, qx, -A * qy);
+    const float gqy = fmaf(Bz, qy, A * xp);
+    const float gqz = -B * rho;
+    acc.ax += gqx; acc.ay += gqy; acc.az += gqz;
+    acc.tx += fmaf(qy, gqz, -qz * gqy);
+    acc.ty += fmaf(qz, gqx, -qx * gqz);
+    acc.tz += fmaf(qx, gqy, -qy * gqx);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pose set-up and gradient finish (one thread per pose)
+// ---------------------------------------------------------------------------------------------
+PCL_HD void pcl_pose_from_params(const float* p6, PclPose& P) {
+  // R = (Rz·Ry)·Rx in fp32 like the reference's two torch.mm calls (omniloc.py:187-188)
+  const float cy = cosf(p6[3]), sy = sinf(p6[3]);
+  const float cp = cosf(p6[4]), sp = sinf(p6[4]);
+  const float cr = cosf(p6[5]), sr = sinf(p6[5]);
+  const float m00 = cy * cp, m01 = -sy, m02 = cy * sp;
+  const float m10 = sy * cp, m11 = cy, m12 = sy * sp;
+  const float m20 = -sp, m21 = 0.0f, m22 = cp;
+  P.r00 = m00; P.r01 = m01 * cr + m02 * sr; P.r02 = m02 * cr - m01 * sr;
+  P.r10 = m10; P.r11 = m11 * cr + m12 * sr; P.r12 = m12 * cr - m11 * sr;
+  P.r20 = m20; P.r21 = m21 * cr + m22 * sr; P.r22 = m22 * cr - m21 * sr;
+  P.tx = p6[0]; P.ty = p6[1]; P.tz = p6[2];
+}
+
+// sums[8] = {Σ m e, Σ m, a(3), τ(3)} (already reduced over all points)  ->  loss, grad[6]
+PCL_HD void pcl_finish_gradient(const float* p6, const PclPose& P, const PclImage& I, const double* sums,
+                                float* loss, float* count, float* grad6) {
+  const double M = sums[1];
+  *loss = (float)(sums[0] / M);               // 0/0 -> NaN, the reference's empty mean
+  if (count) *count = (float)M;
+  if (!grad6) return;
+  const double k = (double)I.tex_scale / M;   // g_s carries tex_scale (sample is s·tex_scale)
+  const double ax = sums[2] * k, ay = sums[3] * k, az = sums[4] * k;
+  const double tx = sums[5] * k, ty = sums[6] * k, tz = sums[7] * k;
+  // dL/dt = -Rᵀ a
+  grad6[0] = (float)(-(P.r00 * ax + P.r10 * ay + P.r20 * az));
+  grad6[1] = (float)(-(P.r01 * ax + P.r11 * ay + P.r21 * az));
+  grad6[2] = (float)(-(P.r02 * ax + P.r12 * ay + P.r22 * az));
+  // dL/dangle = ω·τ with ω_yaw = z, ω_pitch = Rz·y, ω_roll = Rz·Ry·x
+  const double cy = cos((double)p6[3]), sy = sin((double)p6[3]);
+  const double cp = cos((double)p6[4]), sp = sin((double)p6[4]);
+  grad6[3] = (float)tz;
+  grad6[4] = (float)(-sy * tx + cy * ty);
+  grad6[5] = (float)(cy * cp * tx + sy * cp * ty - sp * tz);
+}

@@ -1,0 +1,292 @@
+// Handles: coloured point cloud (SoA, optional Morton order, clamp box), panorama texel tables, top-k.
+// One-off set-up work per room / per query (localize.py:159-164, :169-170; utils.py:208-229, :501-502);
+// the radix sorts use CUB (library code, not on the per-iteration path).
+#include "pcl_common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <float.h>
+#include <stdlib.h>
+#include <string.h>
+
+// ------------------------------------------------------------------------------------------------
+// cloud
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int pcl_float_order(float f) {        // monotone float -> uint
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float pcl_float_unorder(unsigned int u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void pcl_bbox_kernel(const float* __restrict__ xyz, long long n, unsigned int* mm /*[6]: min3,max3*/) {
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { const float v = xyz[3 * i + k]; lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v); }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&mm[k], pcl_float_order(lo[k])); atomicMax(&mm[3 + k], pcl_float_order(hi[k])); }
+  }
+}
+
+__device__ __forceinline__ unsigned long long pcl_spread21(unsigned long long v) {   // 21 bits -> every third bit
+  v &= 0x1fffffull;
+  v = (v | (v << 32)) & 0x1f00000000ffffull;
+  v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+  v = (v | (v << 8)) & 0x100f00f00f00f00full;
+  v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+  v = (v | (v << 2)) & 0x1249249249249249ull;
+  return v;
+}
+
+__global__ void pcl_morton_kernel(const float* __restrict__ xyz, long long n, const unsigned int* mm,
+                                  unsigned long long* keys, unsigned int* idx) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long code = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float lo = pcl_float_unorder(mm[k]), hi = pcl_float_unorder(mm[3 + k]);
+    const float ext = fmaxf(hi - lo, 1e-20f);
+    float t = (xyz[3 * i + k] - lo) / ext;
+    t = fminf(fmaxf(t, 0.0f), 1.0f);
+    const unsigned long long qv = (unsigned long long)(t * 2097151.0f);
+    code |= pcl_spread21(qv) << k;
+  }
+  keys[i] = code;
+  idx[i] = (unsigned int)i;
+}
+
+__global__ void pcl_gather_kernel(const float* __restrict__ xyz, const float* __restrict__ rgb, const unsigned int* __restrict__ perm,
+                                  long long n, float* x, float* y, float* z, float* r, float* g, float* b) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long s = perm ? (long long)perm[i] : i;
+  x[i] = xyz[3 * s]; y[i] = xyz[3 * s + 1]; z[i] = xyz[3 * s + 2];
+  r[i] = rgb[3 * s]; g[i] = rgb[3 * s + 1]; b[i] = rgb[3 * s + 2];
+}
+
+extern "C" int pcl_cloud_create(const float* xyz, const float* rgb, int64_t n, double q, int order, void* stream, pcl_cloud** out) {
+  if (!xyz || !rgb || !out || n <= 0 || n > 0xfffffff0ll) { pcl_set_error("bad cloud arguments (n=%lld)", (long long)n); return PCL_ERR_INVALID; }
+  if (!(q >= 0.0 && q <= 1.0)) { pcl_set_error("quantile %g outside [0,1]", q); return PCL_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  pcl_cloud* c = (pcl_cloud*)calloc(1, sizeof(pcl_cloud));
+  c->n = n;
+  c->n_pad = (n + PCL_TILE_ALIGN - 1) / PCL_TILE_ALIGN * PCL_TILE_ALIGN;
+  c->order = order;
+  PCL_CUDA(cudaMalloc((void**)&c->block, sizeof(float) * 6 * (size_t)c->n_pad));
+  PCL_CUDA(cudaMemsetAsync(c->block, 0, sizeof(float) * 6 * (size_t)c->n_pad, st));
+  c->x = c->block; c->y = c->x + c->n_pad; c->z = c->y + c->n_pad;
+  c->r = c->z + c->n_pad; c->g = c->r + c->n_pad; c->b = c->g + c->n_pad;
+
+  const int threads = 256;
+  const int blocks = (int)((n + threads - 1) / threads);
+  unsigned int* perm = nullptr;
+  void* scratch = nullptr;
+  if (order == PCL_CLOUD_MORTON) {
+    unsigned int* mm; unsigned long long *k_in, *k_out; unsigned int *v_in, *v_out;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                    (unsigned int*)nullptr, (unsigned int*)nullptr, (int)n, 0, 63, st);
+    const size_t nb = (size_t)n;
+    const size_t total = 64 + nb * 8 * 2 + nb * 4 * 2 + tmp_bytes + 256;
+    PCL_CUDA(cudaMalloc(&scratch, total));
+    char* pch = (char*)scratch;
+    mm = (unsigned int*)pch; pch += 64;
+    k_in = (unsigned long long*)pch; pch += nb * 8;
+    k_out = (unsigned long long*)pch; pch += nb * 8;
+    v_in = (unsigned int*)pch; pch += nb * 4;
+    v_out = (unsigned int*)pch; pch += nb * 4;
+    pch = (char*)(((uintptr_t)pch + 255) & ~(uintptr_t)255);
+    const unsigned int init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    PCL_CUDA(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    pcl_bbox_kernel<<<blocks < 1184 ? blocks : 1184, threads, 0, st>>>(xyz, n, mm);
+    PCL_LAUNCH_CHECK();
+    pcl_morton_kernel<<<blocks, threads, 0, st>>>(xyz, n, mm, k_in, v_in);
+    PCL_LAUNCH_CHECK();
+    PCL_CUDA(cub::DeviceRadixSort::SortPairs(pch, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, 63, st));
+    perm = v_out;
+  }
+  pcl_gather_kernel<<<blocks, threads, 0, st>>>(xyz, rgb, perm, n, c->x, c->y, c->z, c->r, c->g, c->b);
+  PCL_LAUNCH_CHECK();
+
+  // clamp box: order statistics int(N q), int(N (1-q)) per axis (utils.py:222-227)
+  {
+    long long i_lo = (long long)((double)n * q), i_hi = (long long)((double)n * (1.0 - q));
+    if (i_lo > n - 1) i_lo = n - 1;
+    if (i_hi > n - 1) i_hi = n - 1;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (float*)nullptr, (float*)nullptr, (int)n, 0, 32, st);
+    void* tmp = nullptr; float* sorted = nullptr;
+    PCL_CUDA(cudaMalloc(&tmp, tmp_bytes + 256));
+    PCL_CUDA(cudaMalloc((void**)&sorted, sizeof(float) * (size_t)n));
+    const float* axes[3] = {c->x, c->y, c->z};
+    for (int k = 0; k < 3; ++k) {
+      PCL_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, axes[k], sorted, (int)n, 0, 32, st));
+      PCL_CUDA(cudaMemcpyAsync(&c->lo_hi[k], sorted + i_lo, sizeof(float), cudaMemcpyDeviceToHost, st));
+      PCL_CUDA(cudaMemcpyAsync(&c->lo_hi[3 + k], sorted + i_hi, sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    PCL_CUDA(cudaStreamSynchronize(st));
+    cudaFree(tmp); cudaFree(sorted);
+  }
+  if (scratch) cudaFree(scratch);
+  *out = c;
+  return PCL_OK;
+}
+
+extern "C" int64_t pcl_cloud_size(const pcl_cloud* c) { return c ? c->n : 0; }
+
+extern "C" int pcl_cloud_bounds(const pcl_cloud* c, float* lo_hi) {
+  if (!c || !lo_hi) { pcl_set_error("null cloud or output"); return PCL_ERR_INVALID; }
+  memcpy(lo_hi, c->lo_hi, sizeof(float) * 6);
+  return PCL_OK;
+}
+
+extern "C" void pcl_cloud_destroy(pcl_cloud* c) {
+  if (!c) return;
+  cudaFree(c->block);
+  free(c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// image
+// ------------------------------------------------------------------------------------------------
+__global__ void pcl_u8_exact_kernel(const float* __restrict__ img, long long n, int* not_exact) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = img[i];
+  const float b = rintf(v * 255.0f);
+  const bool ok = (b >= 0.0f) && (b <= 255.0f) && ((b / 255.0f == v) || ((float)((double)b / 255.0) == v));
+  if (!ok) *not_exact = 1;
+}
+
+__device__ __forceinline__ unsigned int pcl_pack_texel(const float* __restrict__ img, int H, int W, int y, int x) {
+  if (x < 0 || y < 0 || x >= W || y >= H) return 0u;
+  const float* p = img + ((size_t)y * W + x) * 3;
+  const unsigned int r = (unsigned int)rintf(p[0] * 255.0f), g = (unsigned int)rintf(p[1] * 255.0f), b = (unsigned int)rintf(p[2] * 255.0f);
+  return r | (g << 8) | (b << 16);
+}
+
+// quad table: entry (y0+1, x0+1), y0 in [-1,H-1], x0 in [-1,W-1] = {nw, ne, sw, se}
+__global__ void pcl_build_u8q_kernel(const float* __restrict__ img, int H, int W, uint4* tab) {
+  const int xe = blockIdx.x * blockDim.x + threadIdx.x, ye = blockIdx.y;
+  if (xe > W) return;
+  const int x0 = xe - 1, y0 = ye - 1;
+  uint4 e;
+  e.x = pcl_pack_texel(img, H, W, y0, x0); e.y = pcl_pack_texel(img, H, W, y0, x0 + 1);
+  e.z = pcl_pack_texel(img, H, W, y0 + 1, x0); e.w = pcl_pack_texel(img, H, W, y0 + 1, x0 + 1);
+  tab[(size_t)ye * (W + 1) + xe] = e;
+}
+
+// plain tables with a one-texel zero border: entry (y+1, x+1), y in [-1,H], x in [-1,W]
+__global__ void pcl_build_u8p_kernel(const float* __restrict__ img, int H, int W, unsigned int* tab) {
+  const int xe = blockIdx.x * blockDim.x + threadIdx.x, ye = blockIdx.y;
+  if (xe > W + 1) return;
+  tab[(size_t)ye * (W + 2) + xe] = pcl_pack_texel(img, H, W, ye - 1, xe - 1);
+}
+
+__global__ void pcl_build_f32_kernel(const float* __restrict__ img, int H, int W, float4* tab) {
+  const int xe = blockIdx.x * blockDim.x + threadIdx.x, ye = blockIdx.y;
+  if (xe > W + 1) return;
+  const int x = xe - 1, y = ye - 1;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (x >= 0 && y >= 0 && x < W && y < H) { const float* p = img + ((size_t)y * W + x) * 3; v = make_float4(p[0], p[1], p[2], 0.f); }
+  tab[(size_t)ye * (W + 2) + xe] = v;
+}
+
+extern "C" int pcl_image_create(const float* img, int h, int w, int format, void* stream, pcl_image** out) {
+  if (!img || !out || h < 2 || w < 2 || h > 32768 || w > 65536) { pcl_set_error("bad image arguments (%d x %d)", h, w); return PCL_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  int fmt = format;
+  if (fmt == PCL_IMAGE_AUTO || fmt == PCL_IMAGE_U8Q || fmt == PCL_IMAGE_U8P) {
+    int* flag; int host_flag = 0;
+    PCL_CUDA(cudaMalloc((void**)&flag, sizeof(int)));
+    PCL_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    const long long nv = (long long)h * w * 3;
+    pcl_u8_exact_kernel<<<(unsigned int)((nv + 255) / 256), 256, 0, st>>>(img, nv, flag);
+    PCL_LAUNCH_CHECK();
+    PCL_CUDA(cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PCL_CUDA(cudaStreamSynchronize(st));
+    cudaFree(flag);
+    if (host_flag) {
+      if (fmt != PCL_IMAGE_AUTO) { pcl_set_error("image is not exactly uint8/255: a u8 texel table would change the result"); return PCL_ERR_FORMAT; }
+      fmt = PCL_IMAGE_F32;
+    } else if (fmt == PCL_IMAGE_AUTO) {
+      const size_t qbytes = (size_t)(h + 1) * (w + 1) * 16;
+      fmt = (qbytes <= (size_t)80 << 20) ? PCL_IMAGE_U8Q : PCL_IMAGE_U8P;   // keep the table L2-resident (126 MB L2)
+    }
+  } else if (fmt != PCL_IMAGE_F32) {
+    pcl_set_error("unknown image format %d", format);
+    return PCL_ERR_INVALID;
+  }
+  pcl_image* im = (pcl_image*)calloc(1, sizeof(pcl_image));
+  pcl_image_set_geometry(im->view, h, w);
+  im->view.fmt = fmt;
+  dim3 block(128), grid((w + 2 + 127) / 128, 1);
+  if (fmt == PCL_IMAGE_U8Q) {
+    im->bytes = (size_t)(h + 1) * (w + 1) * 16; im->view.pitch = w + 1; im->view.tex_scale = 1.0f / 255.0f;
+    PCL_CUDA(cudaMalloc(&im->data, im->bytes));
+    grid.y = h + 1;
+    pcl_build_u8q_kernel<<<grid, block, 0, st>>>(img, h, w, (uint4*)im->data);
+  } else if (fmt == PCL_IMAGE_U8P) {
+    im->bytes = (size_t)(h + 2) * (w + 2) * 4; im->view.pitch = w + 2; im->view.tex_scale = 1.0f / 255.0f;
+    PCL_CUDA(cudaMalloc(&im->data, im->bytes));
+    grid.y = h + 2;
+    pcl_build_u8p_kernel<<<grid, block, 0, st>>>(img, h, w, (unsigned int*)im->data);
+  } else {
+    im->bytes = (size_t)(h + 2) * (w + 2) * 16; im->view.pitch = w + 2; im->view.tex_scale = 1.0f;
+    PCL_CUDA(cudaMalloc(&im->data, im->bytes));
+    grid.y = h + 2;
+    pcl_build_f32_kernel<<<grid, block, 0, st>>>(img, h, w, (float4*)im->data);
+  }
+  PCL_LAUNCH_CHECK();
+  PCL_CUDA(cudaStreamSynchronize(st));
+  im->view.data = im->data;
+  *out = im;
+  return PCL_OK;
+}
+
+extern "C" int pcl_image_format(const pcl_image* im) { return im ? im->view.fmt : PCL_ERR_INVALID; }
+
+extern "C" void pcl_image_destroy(pcl_image* im) {
+  if (!im) return;
+  cudaFree(im->data);
+  free(im);
+}
+
+// ------------------------------------------------------------------------------------------------
+// top-k (ascending, ties -> lower index, NaN last): stable radix sort of canonicalised keys
+// ------------------------------------------------------------------------------------------------
+__global__ void pcl_topk_keys_kernel(const float* __restrict__ loss, long long n, float* keys, long long* idx) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = loss[i];
+  keys[i] = isnan(v) ? __uint_as_float(0x7fc00000u) : (v == 0.0f ? 0.0f : v);
+  idx[i] = i;
+}
+
+extern "C" int pcl_topk(const float* loss, int64_t p, int k, int64_t* idx_k, void* stream) {
+  if (!loss || !idx_k || p <= 0 || k <= 0 || p > 0x7fffffffll) { pcl_set_error("bad top-k arguments"); return PCL_ERR_INVALID; }
+  if (k > p) k = (int)p;
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (float*)nullptr, (float*)nullptr, (long long*)nullptr, (long long*)nullptr, (int)p, 0, 32, st);
+  const size_t np = (size_t)p;
+  const size_t off_tmp = (np * 4 * 2 + np * 8 * 2 + 255) & ~(size_t)255;
+  char* buf;
+  PCL_CUDA(cudaMallocAsync((void**)&buf, off_tmp + tmp_bytes + 256, st));
+  float* k_in = (float*)buf; float* k_out = k_in + np;
+  long long* v_in = (long long*)(buf + np * 8); long long* v_out = v_in + np;
+  pcl_topk_keys_kernel<<<(unsigned int)((p + 255) / 256), 256, 0, st>>>(loss, p, k_in, v_in);
+  PCL_LAUNCH_CHECK();
+  PCL_CUDA(cub::DeviceRadixSort::SortPairs(buf + off_tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)p, 0, 32, st));
+  PCL_CUDA(cudaMemcpyAsync(idx_k, v_out, sizeof(long long) * (size_t)k, cudaMemcpyDeviceToDevice, st));
+  PCL_CUDA(cudaFreeAsync(buf, st));
+  return PCL_OK;
+}

@@ -1,0 +1,379 @@
+// Sampling-loss kernels: forward-only scoring, fused forward+backward, fused refinement step.
+//
+// One kernel template does all three.  Work decomposition (B200: 148 SMs):
+//   grid.y  = pose blocks (<= PCL_MAX_POSE_BLOCK poses, their R|t live in shared memory)
+//   grid.x  = point chunks; a CTA walks tiles of 256*K points (tile, tile+grid.x, ...)
+//   thread  = K points held in registers (SoA, coalesced 32-bit loads; lane i <-> point i, so with a
+//             Morton-ordered cloud the 32 lanes of a warp gather texels from one small image patch)
+//   per (tile, pose): K evaluations per thread, warp-shuffle reduction, lane 0 accumulates into the
+//             warp's private shared-memory row (no atomics on the hot loop)
+//   per CTA: one row of partial sums per pose to global memory; the LAST CTA of a pose block
+//             (ticket counter) reduces the rows in fixed order (deterministic) in fp64 and finishes:
+//             loss (score) | loss + 6-DoF gradient | loss + gradient + Adam + plateau + clamp (refine)
+//
+// Replaces: utils.py:484-499 (grid scoring), omniloc.py:171-202 / :311-356 (+ autograd backward),
+//           omniloc.py:44-58 / :249-269 (optimiser step, scheduler step, clamp).
+#include "pcl_common.cuh"
+
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+// ------------------------------------------------------------------------------------------------
+// error / bookkeeping
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_pcl_launches{0};
+
+void pcl_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* pcl_last_error(void) { return g_err; }
+extern "C" int pcl_abi_version(void) { return PCL_ABI_VERSION; }
+extern "C" int64_t pcl_launch_count(void) { return (int64_t)g_pcl_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pcl_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// torch.optim.Adam (single-tensor path, betas 0.9/0.999, eps 1e-8) + ReduceLROnPlateau(mode=min,
+// threshold=1e-4 rel, cooldown 0, min_lr 0, eps 1e-8) + translation clamp; one thread per candidate.
+// fp32 tensors, fp64 python scalars — exactly the split torch has (omniloc.py:33,37,49-58).
+__device__ void pcl_refine_update(PclRefineState& st, float* evalp, const float* g, float loss, const PclFinalize& fin) {
+  st.last_loss = loss;
+  st.step += 1;
+  const double bc1 = 1.0 - pow(0.9, (double)st.step);
+  const double bc2 = 1.0 - pow(0.999, (double)st.step);
+  const float step_size = (float)(st.lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  const float w1 = (float)(1.0 - 0.9), b2 = 0.999f, w2 = (float)(1.0 - 0.999);
+  float newp[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float gi = g[i];
+    const float m = st.m[i] + w1 * (gi - st.m[i]);              // exp_avg.lerp_(grad, 1-beta1)
+    const float v = st.v[i] * b2 + (w2 * gi) * gi;              // mul_(beta2).addcmul_(g, g, 1-beta2)
+    st.m[i] = m; st.v[i] = v;
+    const float denom = sqrtf(v) / bc2_sqrt + 1e-8f;
+    newp[i] = st.param[i] - step_size * (m / denom);            // addcdiv_(m, denom, value=-step_size)
+  }
+  // scheduler.step(loss)
+  const double cur = (double)loss;
+  if (cur < st.best * (1.0 - 1e-4)) { st.best = cur; st.bad = 0; } else { st.bad += 1; }
+  if (st.bad > fin.patience) {
+    const double new_lr = fmax(st.lr * fin.factor, 0.0);
+    if (st.lr - new_lr > 1e-8) st.lr = new_lr;
+    st.bad = 0;
+  }
+  // clamp translation into the quantile box; batch semantics evaluates the pre-clamp copy next
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    float c = newp[i];
+    if (i < 3) c = fminf(fmaxf(c, fin.lo[i]), fin.hi[i]);
+    st.param[i] = c;
+    evalp[i] = fin.batch_semantics ? newp[i] : c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int FMT, bool BWD, int K>
+__global__ void __launch_bounds__(PCL_THREADS, BWD ? 2 : 3)
+pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, const int P, const int PB,
+                  const int n_tiles, float* __restrict__ partial, unsigned int* __restrict__ counters, const PclFinalize fin) {
+  constexpr int NS = BWD ? PCL_NSUM : 2;
+  __shared__ __align__(16) PclPose s_pose[PCL_MAX_POSE_BLOCK];
+  __shared__ float s_acc[PCL_WARPS][PCL_MAX_POSE_BLOCK][NS];
+  __shared__ double s_sum[PCL_MAX_POSE_BLOCK][PCL_NSUM];
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p0 = blockIdx.y * PB;
+  const int np = min(PB, P - p0);
+
+  if (tid < np) pcl_pose_from_params(poses6 + 6 * (size_t)(p0 + tid), s_pose[tid]);
+  for (int i = tid; i < PCL_WARPS * PCL_MAX_POSE_BLOCK * NS; i += PCL_THREADS) (&s_acc[0][0][0])[i] = 0.0f;
+  __syncthreads();
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long base = (long long)tile * (PCL_THREADS * K) + tid;
+    float px[K], py[K], pz[K], cr[K], cg[K], cb[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const long long i = base + (long long)j * PCL_THREADS;     // arrays are padded: always in bounds
+      px[j] = __ldg(C.x + i); py[j] = __ldg(C.y + i); pz[j] = __ldg(C.z + i);
+      cr[j] = __ldg(C.r + i); cg[j] = __ldg(C.g + i); cb[j] = __ldg(C.b + i);
+    }
+    for (int p = 0; p < np; ++p) {
+      const PclPose pose = s_pose[p];
+      PclAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const bool valid = (base + (long long)j * PCL_THREADS) < C.n;
+        pcl_eval<FMT, BWD>(pose, I, px[j], py[j], pz[j], cr[j], cg[j], cb[j], valid, acc);
+      }
+      float v[NS];
+      v[0] = pcl_warp_sum(acc.se); v[1] = pcl_warp_sum(acc.sm);
+      if (BWD) {
+        v[2] = pcl_warp_sum(acc.ax); v[3] = pcl_warp_sum(acc.ay); v[4] = pcl_warp_sum(acc.az);
+        v[5] = pcl_warp_sum(acc.tx); v[6] = pcl_warp_sum(acc.ty); v[7] = pcl_warp_sum(acc.tz);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) s_acc[warp][p][s] += v[s];
+      }
+    }
+  }
+  __syncthreads();
+
+  // CTA partial row: partial[blockIdx.x][s][pose]
+  for (int i = tid; i < np * NS; i += PCL_THREADS) {
+    const int s = i / np, p = i - s * np;
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < PCL_WARPS; ++w) t += s_acc[w][p][s];
+    partial[((size_t)blockIdx.x * NS + s) * (size_t)P + (size_t)(p0 + p)] = t;
+  }
+
+  // last-block-done
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int ticket = atomicAdd(&counters[blockIdx.y], 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+
+  for (int i = tid; i < np * NS; i += PCL_THREADS) {
+    const int s = i / np, p = i - s * np;
+    double t = 0.0;
+    for (unsigned int bx = 0; bx < gridDim.x; ++bx)
+      t += (double)__ldcg(partial + ((size_t)bx * NS + s) * (size_t)P + (size_t)(p0 + p));
+    s_sum[p][s] = t;
+  }
+  __syncthreads();
+  if (tid < np) {
+    const int pg = p0 + tid;
+    const float* p6 = poses6 + 6 * (size_t)pg;
+    float loss, cnt, grad[6];
+    pcl_finish_gradient(p6, s_pose[tid], I, s_sum[tid], &loss, &cnt, BWD ? grad : nullptr);
+    if (fin.loss) fin.loss[pg] = loss;
+    if (fin.count) fin.count[pg] = cnt;
+    if (BWD) {
+      if (fin.mode == PCL_FIN_GRAD) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) fin.grad[6 * (size_t)pg + i] = grad[i];
+      } else if (fin.mode == PCL_FIN_REFINE) {
+        pcl_refine_update(fin.state[pg], fin.evalp + 6 * (size_t)pg, grad, loss, fin);
+      }
+    }
+  }
+  if (tid == 0) counters[blockIdx.y] = 0u;     // self-resetting: the next launch needs no memset
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launch
+// ------------------------------------------------------------------------------------------------
+struct PclLaunchPlan { int K, PB, gx, gy, n_tiles, NS; };
+
+static int pcl_env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+static int pcl_num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  }
+  return sms;
+}
+
+static PclLaunchPlan pcl_plan(const pcl_cloud* c, int64_t P, bool bwd) {
+  PclLaunchPlan pl;
+  pl.K = pcl_env_int("PCL_K", 4);
+  if (pl.K != 4 && pl.K != 8 && pl.K != 2) pl.K = 4;
+  pl.NS = bwd ? PCL_NSUM : 2;
+  pl.PB = (int)(P < PCL_MAX_POSE_BLOCK ? P : PCL_MAX_POSE_BLOCK);
+  const int pb_env = pcl_env_int(bwd ? "PCL_PB_BWD" : "PCL_PB_FWD", 0);
+  if (pb_env > 0 && pb_env <= PCL_MAX_POSE_BLOCK) pl.PB = (int)(pb_env < P ? pb_env : P);
+  pl.gy = (int)((P + pl.PB - 1) / pl.PB);
+  pl.n_tiles = (int)(c->n_pad / (PCL_THREADS * pl.K));
+  const int resident = pcl_num_sms() * (bwd ? 2 : 3);
+  const int waves = pcl_env_int("PCL_WAVES", 4);
+  int gx = (resident * waves + pl.gy - 1) / pl.gy;
+  if (gx < 1) gx = 1;
+  if (gx > pl.n_tiles) gx = pl.n_tiles;
+  const int per = (pl.n_tiles + gx - 1) / gx;        // tiles per CTA, then the fewest CTAs giving it
+  pl.gx = (pl.n_tiles + per - 1) / per;
+  return pl;
+}
+
+template <int FMT, bool BWD>
+static void pcl_launch_fmt(const PclLaunchPlan& pl, const PclCloudView& C, const PclImage& I, const float* poses, int P,
+                           float* partial, unsigned int* counters, const PclFinalize& fin, cudaStream_t st) {
+  dim3 grid(pl.gx, pl.gy), block(PCL_THREADS);
+  switch (pl.K) {
+    case 2: pcl_sample_kernel<FMT, BWD, 2><<<grid, block, 0, st>>>(C, I, poses, P, pl.PB, pl.n_tiles, partial, counters, fin); break;
+    case 8: pcl_sample_kernel<FMT, BWD, 8><<<grid, block, 0, st>>>(C, I, poses, P, pl.PB, pl.n_tiles, partial, counters, fin); break;
+    default: pcl_sample_kernel<FMT, BWD, 4><<<grid, block, 0, st>>>(C, I, poses, P, pl.PB, pl.n_tiles, partial, counters, fin); break;
+  }
+}
+
+template <bool BWD>
+static int pcl_launch(const PclLaunchPlan& pl, const pcl_cloud* c, const pcl_image* im, const float* poses, int P,
+                      float* partial, unsigned int* counters, const PclFinalize& fin, cudaStream_t st) {
+  PclCloudView C = {c->x, c->y, c->z, c->r, c->g, c->b, (long long)c->n};
+  switch (im->view.fmt) {
+    case PCL_FMT_U8Q: pcl_launch_fmt<PCL_FMT_U8Q, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st); break;
+    case PCL_FMT_U8P: pcl_launch_fmt<PCL_FMT_U8P, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st); break;
+    case PCL_FMT_F32: pcl_launch_fmt<PCL_FMT_F32, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st); break;
+    default: pcl_set_error("unknown image format %d", im->view.fmt); return PCL_ERR_INVALID;
+  }
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
+
+static int pcl_check_inputs(const pcl_cloud* c, const pcl_image* im, const void* poses, int64_t P) {
+  if (!c || !im || !poses) { pcl_set_error("null handle or pose pointer"); return PCL_ERR_INVALID; }
+  if (P <= 0 || P > (1 << 24)) { pcl_set_error("pose count %lld out of range", (long long)P); return PCL_ERR_INVALID; }
+  return PCL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: scoring, loss+gradient
+// ------------------------------------------------------------------------------------------------
+static int pcl_run_once(const pcl_cloud* c, const pcl_image* im, const float* poses, int64_t P, bool bwd,
+                        float* loss, float* count, float* grad, cudaStream_t st) {
+  const PclLaunchPlan pl = pcl_plan(c, P, bwd);
+  float* partial = nullptr;
+  unsigned int* counters = nullptr;
+  const size_t pbytes = (size_t)pl.gx * pl.NS * (size_t)P * sizeof(float);
+  PCL_CUDA(cudaMallocAsync((void**)&partial, pbytes + (size_t)pl.gy * sizeof(unsigned int), st));
+  counters = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(partial) + pbytes);
+  PCL_CUDA(cudaMemsetAsync(counters, 0, (size_t)pl.gy * sizeof(unsigned int), st));
+  PclFinalize fin;
+  memset(&fin, 0, sizeof(fin));
+  fin.mode = bwd ? PCL_FIN_GRAD : PCL_FIN_SCORE;
+  fin.loss = loss; fin.count = count; fin.grad = grad;
+  int rc = bwd ? pcl_launch<true>(pl, c, im, poses, (int)P, partial, counters, fin, st)
+               : pcl_launch<false>(pl, c, im, poses, (int)P, partial, counters, fin, st);
+  PCL_CUDA(cudaFreeAsync(partial, st));
+  return rc;
+}
+
+extern "C" int pcl_score(const pcl_cloud* c, const pcl_image* im, const float* poses_p6_dev, int64_t p,
+                         float* loss_p_dev, float* count_p_dev, void* stream) {
+  int rc = pcl_check_inputs(c, im, poses_p6_dev, p);
+  if (rc) return rc;
+  if (!loss_p_dev) { pcl_set_error("loss output is null"); return PCL_ERR_INVALID; }
+  return pcl_run_once(c, im, poses_p6_dev, p, false, loss_p_dev, count_p_dev, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int pcl_loss_fwd_bwd(const pcl_cloud* c, const pcl_image* im, const float* poses_b6_dev, int b,
+                                float* loss_b_dev, float* count_b_dev, float* grad_b6_dev, void* stream) {
+  int rc = pcl_check_inputs(c, im, poses_b6_dev, b);
+  if (rc) return rc;
+  if (!loss_b_dev || !grad_b6_dev) { pcl_set_error("loss/grad output is null"); return PCL_ERR_INVALID; }
+  return pcl_run_once(c, im, poses_b6_dev, b, true, loss_b_dev, count_b_dev, grad_b6_dev, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: fused refinement
+// ------------------------------------------------------------------------------------------------
+__global__ void pcl_refine_reset_kernel(PclRefineState* st, float* evalp, const float* poses6, int B, double lr) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  PclRefineState s;
+  for (int i = 0; i < 6; ++i) { s.m[i] = 0.f; s.v[i] = 0.f; s.param[i] = poses6[6 * b + i]; evalp[6 * b + i] = poses6[6 * b + i]; }
+  s.last_loss = nanf(""); s.step = 0; s.bad = 0; s.pad = 0; s.lr = lr; s.best = INFINITY;
+  st[b] = s;
+}
+
+__global__ void pcl_refine_read_kernel(const PclRefineState* st, const float* evalp, int B, int batch, float* pose, float* param,
+                                       float* loss, double* lr) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int i = 0; i < 6; ++i) {
+    // sequential semantics returns the clamped parameter; batch semantics the pre-clamp copy (omniloc.py:260,272)
+    if (pose) pose[6 * b + i] = batch ? evalp[6 * b + i] : st[b].param[i];
+    if (param) param[6 * b + i] = st[b].param[i];
+  }
+  if (loss) loss[b] = st[b].last_loss;
+  if (lr) lr[b] = st[b].lr;
+}
+
+extern "C" int pcl_refine_create(int b, double lr, double factor, int patience, int batch_semantics, pcl_refine** out) {
+  if (!out || b <= 0 || b > 65536) { pcl_set_error("bad refine batch %d", b); return PCL_ERR_INVALID; }
+  pcl_refine* r = (pcl_refine*)calloc(1, sizeof(pcl_refine));
+  r->B = b; r->lr0 = lr; r->factor = factor; r->patience = patience; r->batch_semantics = batch_semantics ? 1 : 0;
+  const int gy_max = b;                 // PB >= 1
+  PCL_CUDA(cudaMalloc((void**)&r->state, sizeof(PclRefineState) * b));
+  PCL_CUDA(cudaMalloc((void**)&r->evalp, sizeof(float) * 6 * b));
+  PCL_CUDA(cudaMalloc((void**)&r->loss, sizeof(float) * b));
+  PCL_CUDA(cudaMalloc((void**)&r->counters, sizeof(unsigned int) * gy_max));
+  PCL_CUDA(cudaMemset(r->counters, 0, sizeof(unsigned int) * gy_max));
+  r->partial = nullptr; r->partial_floats = 0;
+  *out = r;
+  return PCL_OK;
+}
+
+extern "C" int pcl_refine_reset(pcl_refine* r, const float* poses_b6_dev, void* stream) {
+  if (!r || !poses_b6_dev) { pcl_set_error("null refine handle or poses"); return PCL_ERR_INVALID; }
+  pcl_refine_reset_kernel<<<(r->B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(r->state, r->evalp, poses_b6_dev, r->B, r->lr0);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
+
+extern "C" int pcl_refine_run(pcl_refine* r, const pcl_cloud* c, const pcl_image* im, int num_iter, void* stream) {
+  if (!r) { pcl_set_error("null refine handle"); return PCL_ERR_INVALID; }
+  int rc = pcl_check_inputs(c, im, r->evalp, r->B);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const PclLaunchPlan pl = pcl_plan(c, r->B, true);
+  const size_t need = (size_t)pl.gx * pl.NS * (size_t)r->B;
+  if (need > r->partial_floats) {
+    if (r->partial) { PCL_CUDA(cudaStreamSynchronize(st)); PCL_CUDA(cudaFree(r->partial)); }
+    PCL_CUDA(cudaMalloc((void**)&r->partial, need * sizeof(float)));
+    r->partial_floats = need;
+  }
+  PclFinalize fin;
+  memset(&fin, 0, sizeof(fin));
+  fin.mode = PCL_FIN_REFINE;
+  fin.loss = r->loss; fin.state = r->state; fin.evalp = r->evalp;
+  for (int i = 0; i < 3; ++i) { fin.lo[i] = c->lo_hi[i]; fin.hi[i] = c->lo_hi[3 + i]; }
+  fin.factor = r->factor; fin.patience = r->patience; fin.batch_semantics = r->batch_semantics;
+  for (int it = 0; it < num_iter; ++it) {
+    rc = pcl_launch<true>(pl, c, im, r->evalp, r->B, r->partial, r->counters, fin, st);
+    if (rc) return rc;
+  }
+  return PCL_OK;
+}
+
+extern "C" int pcl_refine_read(const pcl_refine* r, float* pose_b6_dev, float* param_b6_dev, float* loss_b_dev,
+                               double* lr_b_dev, void* stream) {
+  if (!r) { pcl_set_error("null refine handle"); return PCL_ERR_INVALID; }
+  pcl_refine_read_kernel<<<(r->B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(r->state, r->evalp, r->B, r->batch_semantics,
+                                                                                pose_b6_dev, param_b6_dev, loss_b_dev, lr_b_dev);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
+
+extern "C" void pcl_refine_destroy(pcl_refine* r) {
+  if (!r) return;
+  cudaFree(r->state); cudaFree(r->evalp); cudaFree(r->loss); cudaFree(r->counters);
+  if (r->partial) cudaFree(r->partial);
+  free(r);
+}

@@ -1,0 +1,220 @@
+"""Thin torch-facing wrappers over the C ABI: device handles and the three compute calls.
+
+torch is plumbing only (device memory, streams); all arithmetic of the hot path runs in the
+hand-written CUDA kernels of libpiccolo_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+
+import torch
+
+from . import _lib
+
+IMAGE_AUTO, IMAGE_U8Q, IMAGE_F32, IMAGE_U8P = 0, 1, 2, 3
+IMAGE_FORMATS = {"auto": IMAGE_AUTO, "u8q": IMAGE_U8Q, "f32": IMAGE_F32, "u8p": IMAGE_U8P}
+CLOUD_KEEP_ORDER, CLOUD_MORTON = 0, 1
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.PiccoloError(f"{name} must be a CUDA tensor: piccolo_b200 has no CPU path")
+    return t
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _stream(dev) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class Cloud:
+    """Device-resident coloured point cloud in kernel layout (SoA, Morton order) + its clamp box.
+    Replaces the per-room `xyz.to(device)`, `rgb.to(device)` (localize.py:163-164) and the per-iteration
+    `quantile()` calls (omniloc.py:53-55)."""
+
+    def __init__(self, xyz: torch.Tensor, rgb: torch.Tensor, out_of_room_quantile: float = 0.05, order: int = CLOUD_MORTON):
+        lib = _lib.load()
+        _require_cuda(xyz, "xyz"); _require_cuda(rgb, "rgb")
+        if xyz.dim() != 2 or xyz.shape[1] != 3 or rgb.shape != xyz.shape:
+            raise _lib.PiccoloError(f"xyz/rgb must both be (N,3); got {tuple(xyz.shape)} and {tuple(rgb.shape)}")
+        self.device = xyz.device
+        xyz_c, rgb_c = _f32c(xyz), _f32c(rgb)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.pcl_cloud_create(xyz_c.data_ptr(), rgb_c.data_ptr(), xyz_c.shape[0], float(out_of_room_quantile),
+                                            int(order), _stream(self.device), ctypes.byref(h)))
+        self._h = h
+        self.n = int(xyz_c.shape[0])
+        buf = (ctypes.c_float * 6)()
+        _lib.check(lib.pcl_cloud_bounds(self._h, buf))
+        self.box_lo = torch.tensor(list(buf[:3]), dtype=torch.float32)
+        self.box_hi = torch.tensor(list(buf[3:]), dtype=torch.float32)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().pcl_cloud_destroy(h)
+            except Exception:
+                pass
+
+
+class Image:
+    """Device-resident panorama texel table.  Replaces `img.to(device)` (localize.py:170, :213)."""
+
+    def __init__(self, img: torch.Tensor, fmt="auto"):
+        lib = _lib.load()
+        _require_cuda(img, "img")
+        if img.dim() != 3 or img.shape[2] != 3:
+            raise _lib.PiccoloError(f"img must be (H,W,3); got {tuple(img.shape)}")
+        self.device = img.device
+        img_c = _f32c(img)
+        self.H, self.W = int(img_c.shape[0]), int(img_c.shape[1])
+        h = ctypes.c_void_p()
+        code = IMAGE_FORMATS[fmt] if isinstance(fmt, str) else int(fmt)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.pcl_image_create(img_c.data_ptr(), self.H, self.W, code, _stream(self.device), ctypes.byref(h)))
+        self._h = h
+        self.format = int(lib.pcl_image_format(h))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().pcl_image_destroy(h)
+            except Exception:
+                pass
+
+
+def _poses(poses: torch.Tensor) -> torch.Tensor:
+    _require_cuda(poses, "poses")
+    p = _f32c(poses)
+    if p.dim() != 2 or p.shape[1] != 6:
+        raise _lib.PiccoloError(f"poses must be (P,6) = (tx,ty,tz,yaw,pitch,roll); got {tuple(p.shape)}")
+    return p
+
+
+def score(cloud: Cloud, image: Image, poses: torch.Tensor):
+    """Forward-only loss of P poses.  Returns (loss (P,), count (P,)) on the device."""
+    lib = _lib.load()
+    p = _poses(poses)
+    P = p.shape[0]
+    loss = torch.empty(P, dtype=torch.float32, device=p.device)
+    count = torch.empty(P, dtype=torch.float32, device=p.device)
+    if P == 0:
+        return loss, count
+    with torch.cuda.device(p.device):
+        _lib.check(lib.pcl_score(cloud._h, image._h, p.data_ptr(), P, loss.data_ptr(), count.data_ptr(), _stream(p.device)))
+    return loss, count
+
+
+def loss_fwd_bwd(cloud: Cloud, image: Image, poses: torch.Tensor):
+    """Loss and analytic 6-DoF gradient of B poses in one launch.  Returns (loss (B,), count (B,), grad (B,6))."""
+    lib = _lib.load()
+    p = _poses(poses)
+    B = p.shape[0]
+    loss = torch.empty(B, dtype=torch.float32, device=p.device)
+    count = torch.empty(B, dtype=torch.float32, device=p.device)
+    grad = torch.empty(B, 6, dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        _lib.check(lib.pcl_loss_fwd_bwd(cloud._h, image._h, p.data_ptr(), B, loss.data_ptr(), count.data_ptr(), grad.data_ptr(), _stream(p.device)))
+    return loss, count, grad
+
+
+def topk(loss: torch.Tensor, k: int) -> torch.Tensor:
+    """Indices of the k smallest losses (ascending, ties -> lower index, NaN last), int64 on the device."""
+    lib = _lib.load()
+    _require_cuda(loss, "loss")
+    l = _f32c(loss).reshape(-1)
+    k = min(int(k), l.numel())
+    idx = torch.empty(k, dtype=torch.int64, device=l.device)
+    if k == 0:
+        return idx
+    with torch.cuda.device(l.device):
+        _lib.check(lib.pcl_topk(l.data_ptr(), l.numel(), k, idx.data_ptr(), _stream(l.device)))
+    return idx
+
+
+class Refiner:
+    """Fused refinement of B candidates: every iteration is ONE kernel launch doing loss, backward,
+    reduction, Adam, ReduceLROnPlateau and the translation clamp (omniloc.py:44-58, :249-269)."""
+
+    def __init__(self, B: int, lr: float = 0.1, factor: float = 0.9, patience: int = 5, batch_semantics: bool = False):
+        lib = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(lib.pcl_refine_create(int(B), float(lr), float(factor), int(patience), int(bool(batch_semantics)), ctypes.byref(h)))
+        self._h = h
+        self.B = int(B)
+
+    def reset(self, poses: torch.Tensor):
+        p = _poses(poses)
+        if p.shape[0] != self.B:
+            raise _lib.PiccoloError(f"expected {self.B} start poses, got {p.shape[0]}")
+        self.device = p.device
+        with torch.cuda.device(p.device):
+            _lib.check(_lib.load().pcl_refine_reset(self._h, p.data_ptr(), _stream(p.device)))
+        return self
+
+    def run(self, cloud: Cloud, image: Image, num_iter: int):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().pcl_refine_run(self._h, cloud._h, image._h, int(num_iter), _stream(self.device)))
+        return self
+
+    def read(self):
+        """Returns dict(pose (B,6), param (B,6), loss (B,), lr (B,) float64) on the device."""
+        dev = self.device
+        pose = torch.empty(self.B, 6, dtype=torch.float32, device=dev)
+        param = torch.empty(self.B, 6, dtype=torch.float32, device=dev)
+        loss = torch.empty(self.B, dtype=torch.float32, device=dev)
+        lr = torch.empty(self.B, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().pcl_refine_read(self._h, pose.data_ptr(), param.data_ptr(), loss.data_ptr(), lr.data_ptr(), _stream(dev)))
+        return {"pose": pose, "param": param, "loss": loss, "lr": lr}
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().pcl_refine_destroy(h)
+            except Exception:
+                pass
+
+
+# ------------------------------------------------------------------------------------------------
+# handle cache: the reference API passes raw tensors on every call (and builds a new loss module per
+# candidate, omniloc.py:42); re-packing the cloud each time would dominate small queries.
+# ------------------------------------------------------------------------------------------------
+_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_CACHE_SIZE = 8
+
+
+def _key(*tensors, extra=()):
+    return tuple((t.data_ptr(), tuple(t.shape), t._version, str(t.device), t.dtype) for t in tensors) + tuple(extra)
+
+
+def _cached(key, tensors, build):
+    hit = _CACHE.get(key)
+    if hit is not None:
+        _CACHE.move_to_end(key)
+        return hit[0]
+    obj = build()
+    _CACHE[key] = (obj, tensors)        # hold the tensors: their storage cannot be recycled while cached
+    while len(_CACHE) > _CACHE_SIZE:
+        _CACHE.popitem(last=False)
+    return obj
+
+
+def get_cloud(xyz: torch.Tensor, rgb: torch.Tensor, q: float = 0.05) -> Cloud:
+    return _cached(_key(xyz, rgb, extra=("cloud", float(q))), (xyz, rgb), lambda: Cloud(xyz, rgb, q))
+
+
+def get_image(img: torch.Tensor, fmt="auto") -> Image:
+    return _cached(_key(img, extra=("image", fmt)), (img,), lambda: Image(img, fmt))
+
+
+def clear_cache():
+    _CACHE.clear()

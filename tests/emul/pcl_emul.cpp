@@ -1,0 +1,63 @@
+// Host emulation of the device arithmetic in piccolo_b200/csrc/pcl_eval.cuh  —  TEST ONLY.
+// Compiled by tests/test_emul_math.py with g++ so that the per-point maths (projection, bilinear
+// taps, analytic gradient, finish) can be checked against the oracle on a machine without a GPU.
+// The product library never links or loads this file.
+#include <vector>
+#include <cstring>
+#include <cmath>
+#include "../../piccolo_b200/csrc/pcl_eval.cuh"
+
+static inline uint32_t pack_rgba(const float* img, int H, int W, int y, int x) {
+  if (x < 0 || y < 0 || x >= W || y >= H) return 0u;
+  const float* p = img + ((size_t)y * W + x) * 3;
+  uint32_t r = (uint32_t)lrintf(p[0] * 255.0f), g = (uint32_t)lrintf(p[1] * 255.0f), b = (uint32_t)lrintf(p[2] * 255.0f);
+  return r | (g << 8) | (b << 16);
+}
+
+template <int FMT, bool BWD>
+static void run(const PclImage& I, const float* xyz, const float* rgb, long n, const float* poses, int P,
+                float* loss, float* cnt, float* grad) {
+  for (int p = 0; p < P; ++p) {
+    PclPose pose; pcl_pose_from_params(poses + 6 * p, pose);
+    double sums[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long i = 0; i < n; ++i) {
+      PclAcc a; std::memset(&a, 0, sizeof(a));
+      pcl_eval<FMT, BWD>(pose, I, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], true, a);
+      sums[0] += a.se; sums[1] += a.sm; sums[2] += a.ax; sums[3] += a.ay; sums[4] += a.az; sums[5] += a.tx; sums[6] += a.ty; sums[7] += a.tz;
+    }
+    pcl_finish_gradient(poses + 6 * p, pose, I, sums, loss + p, cnt + p, BWD ? grad + 6 * p : nullptr);
+  }
+}
+
+extern "C" int emul_loss_grad(const float* xyz, const float* rgb, long n, const float* img, int H, int W, int fmt,
+                              const float* poses, int P, int bwd, float* loss, float* cnt, float* grad) {
+  PclImage I; std::memset(&I, 0, sizeof(I));
+  pcl_image_set_geometry(I, H, W);
+  I.fmt = fmt;
+  std::vector<uint32_t> u8;
+  std::vector<float> f32;
+  if (fmt == PCL_FMT_U8Q) {
+    I.pitch = W + 1; I.tex_scale = 1.0f / 255.0f;
+    u8.resize((size_t)(H + 1) * (W + 1) * 4);
+    for (int y0 = -1; y0 < H; ++y0) for (int x0 = -1; x0 < W; ++x0) {
+      uint32_t* e = &u8[((size_t)(y0 + 1) * (W + 1) + (x0 + 1)) * 4];
+      e[0] = pack_rgba(img, H, W, y0, x0); e[1] = pack_rgba(img, H, W, y0, x0 + 1);
+      e[2] = pack_rgba(img, H, W, y0 + 1, x0); e[3] = pack_rgba(img, H, W, y0 + 1, x0 + 1);
+    }
+    I.data = u8.data();
+  } else if (fmt == PCL_FMT_U8P) {
+    I.pitch = W + 2; I.tex_scale = 1.0f / 255.0f;
+    u8.resize((size_t)(H + 2) * (W + 2));
+    for (int y = -1; y <= H; ++y) for (int x = -1; x <= W; ++x) u8[(size_t)(y + 1) * (W + 2) + (x + 1)] = pack_rgba(img, H, W, y, x);
+    I.data = u8.data();
+  } else {
+    I.pitch = W + 2; I.tex_scale = 1.0f;
+    f32.assign((size_t)(H + 2) * (W + 2) * 4, 0.0f);
+    for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x)
+      for (int c = 0; c < 3; ++c) f32[((size_t)(y + 1) * (W + 2) + (x + 1)) * 4 + c] = img[((size_t)y * W + x) * 3 + c];
+    I.data = f32.data();
+  }
+#define GO(F) do { if (bwd) run<F, true>(I, xyz, rgb, n, poses, P, loss, cnt, grad); else run<F, false>(I, xyz, rgb, n, poses, P, loss, cnt, grad); } while (0)
+  if (fmt == PCL_FMT_U8Q) GO(PCL_FMT_U8Q); else if (fmt == PCL_FMT_U8P) GO(PCL_FMT_U8P); else GO(PCL_FMT_F32);
+  return 0;
+}

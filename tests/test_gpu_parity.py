@@ -1,0 +1,288 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the reference-facing Python API) against the
+golden vectors of the unmodified reference and against the CPU oracle on seeded inputs.
+
+Gates (BASELINE.json north_star): loss within 1e-4 relative; gradients within
+max(1e-4·‖g64‖∞, ‖g32_ref − g64_ref‖∞) of the reference's fp64 gradient; identical top-K; final poses
+within 1 cm / 0.1 deg."""
+from collections import namedtuple
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import piccolo_oracle as orc
+from piccolo_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-4
+Cfg = namedtuple("Cfg", ["num_input", "lr", "num_iter", "patience", "factor", "out_of_room_quantile"])
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+
+
+def rot_err_deg(Ra, Rb):
+    c = (np.trace(np.asarray(Ra, dtype=np.float64).T @ np.asarray(Rb, dtype=np.float64)) - 1) / 2
+    return np.rad2deg(np.arccos(np.clip(c, -1, 1)))
+
+
+def rot_of(pose):
+    return orc.rot_and_derivs_np(np.asarray(pose[3:6], dtype=np.float64), np.float64)[0]
+
+
+def grad_gate(g, g64, g32):
+    tol = max(1e-4 * np.abs(g64).max(), np.abs(g32 - g64).max())
+    return np.abs(g - g64).max() <= tol, np.abs(g - g64).max(), tol
+
+
+@pytest.fixture(scope="module")
+def small(golden):
+    g = golden("loss_small")
+    g["rgb"] = synth.rgb_from_u8(g["rgb8"])
+    g["img"] = synth.img_from_u8(g["img8"])
+    return g
+
+
+@pytest.mark.parametrize("fmt", ["u8q", "u8p", "f32"])
+@pytest.mark.parametrize("order", [0, 1])
+def test_loss_and_gradient_match_reference(small, fmt, order):
+    from piccolo_b200 import engine
+    cloud = engine.Cloud(cu(small["xyz"]), cu(small["rgb"]), 0.05, order)
+    image = engine.Image(cu(small["img"]), fmt)
+    loss, count, grad = engine.loss_fwd_bwd(cloud, image, cu(small["poses"]))
+    loss, grad = loss.cpu().numpy(), grad.cpu().numpy()
+    np.testing.assert_allclose(loss, small["loss32"], rtol=LOSS_RTOL)
+    for i in range(len(loss)):
+        ok, err, tol = grad_gate(grad[i], small["grad64"][i], small["grad32"][i])
+        assert ok, (i, err, tol)
+    # forward-only kernel agrees with the fused one
+    l2, c2 = engine.score(cloud, image, cu(small["poses"]))
+    np.testing.assert_allclose(l2.cpu().numpy(), loss, rtol=2e-6)
+    np.testing.assert_array_equal(c2.cpu().numpy(), count.cpu().numpy())
+
+
+def test_clamp_box_matches_reference_quantile(small):
+    from piccolo_b200 import engine
+    for order in (0, 1):
+        cloud = engine.Cloud(cu(small["xyz"]), cu(small["rgb"]), 0.05, order)
+        np.testing.assert_array_equal(cloud.box_lo.numpy(), small["box_lo"])
+        np.testing.assert_array_equal(cloud.box_hi.numpy(), small["box_hi"])
+
+
+def test_empty_mask_gives_nan(small):
+    from piccolo_b200 import engine
+    cloud = engine.Cloud(cu(small["xyz"]), cu(small["rgb"]))
+    image = engine.Image(cu(np.zeros_like(small["img"])))
+    loss, count = engine.score(cloud, image, cu(small["poses"][:3]))
+    assert torch.isnan(loss).all() and (count == 0).all()
+    assert np.isnan(small["black_loss"])
+    loss, count, grad = engine.loss_fwd_bwd(cloud, image, cu(small["poses"][:3]))
+    assert torch.isnan(loss).all()
+
+
+def test_image_formats_and_errors(small):
+    from piccolo_b200 import _lib, engine
+    assert engine.Image(cu(small["img"])).format == engine.IMAGE_U8Q
+    noisy = small["img"] + np.float32(1e-3)
+    assert engine.Image(cu(noisy)).format == engine.IMAGE_F32
+    with pytest.raises(_lib.PiccoloError):
+        engine.Image(cu(noisy), "u8q")
+    with pytest.raises(_lib.PiccoloError):
+        engine.Image(torch.from_numpy(small["img"]))           # CPU tensor: no CPU path
+    with pytest.raises(_lib.PiccoloError):
+        engine.score(engine.Cloud(cu(small["xyz"]), cu(small["rgb"])), engine.Image(cu(small["img"])), cu(small["poses"][:, :5]))
+
+
+def test_float_image_matches_oracle(small):
+    """Arbitrary float panorama (not uint8/255) takes the fp32 texel path."""
+    from piccolo_b200 import engine
+    rng = np.random.default_rng(3)
+    img = np.clip(small["img"] * 0.9 + rng.random(small["img"].shape).astype(np.float32) * 0.1, 0, 1).astype(np.float32)
+    rgb = rng.random(small["rgb"].shape).astype(np.float32)
+    cloud = engine.Cloud(cu(small["xyz"]), cu(rgb))
+    image = engine.Image(cu(img))
+    assert image.format == engine.IMAGE_F32
+    loss, count, grad = engine.loss_fwd_bwd(cloud, image, cu(small["poses"][:6]))
+    for i in range(6):
+        l64, m64, g64 = orc.loss_and_grad_np(small["xyz"], rgb, img, small["poses"][i].astype(np.float64), np.float64)
+        l32, m32, g32 = orc.loss_and_grad_np(small["xyz"], rgb, img, small["poses"][i], np.float32)
+        assert abs(loss[i].item() - l64) <= LOSS_RTOL * abs(l64)
+        ok, err, tol = grad_gate(grad[i].cpu().numpy(), g64, g32)
+        assert ok, (i, err, tol)
+
+
+def test_grid_scoring_and_topk_match_trim_input_loss(small, golden):
+    from piccolo_b200 import utils as pu
+    g = golden("score_small")
+    img, xyz, rgb = cu(small["img"]), cu(small["xyz"]), cu(small["rgb"])
+    trans, rot = cu(g["trans"]), cu(g["rot"])
+    table = pu.score_grid(img, xyz, rgb, trans, rot).cpu().numpy().reshape(-1)
+    np.testing.assert_allclose(table, g["loss_table"], rtol=LOSS_RTOL)
+    tt, rr = pu.trim_input_loss(img, xyz, rgb, trans, rot, 10)
+    assert tt.device.type == "cuda"
+    np.testing.assert_array_equal(tt.cpu().numpy(), g["top10_trans"])
+    np.testing.assert_array_equal(rr.cpu().numpy(), g["top10_rot"])
+    tt, rr = pu.trim_input_loss(img, xyz, rgb, trans, rot, 10 ** 6)     # num_input > T*R  ->  everything, sorted
+    np.testing.assert_array_equal(tt.cpu().numpy(), g["all_trans"])
+    np.testing.assert_array_equal(rr.cpu().numpy(), g["all_rot"])
+
+
+def test_topk_ties_nan_and_sizes():
+    from piccolo_b200 import engine
+    loss = np.array([0.5, np.nan, 0.2, 0.2, 0.9, 0.1, -0.0, 0.0], dtype=np.float32)
+    np.testing.assert_array_equal(engine.topk(cu(loss), 5).cpu().numpy(), orc.topk_ascending(loss, 5))
+    np.testing.assert_array_equal(engine.topk(cu(loss), 99).cpu().numpy(), orc.topk_ascending(loss, 99))
+    rng = np.random.default_rng(0)
+    big = np.round(rng.random(100003).astype(np.float32), 3)            # many ties
+    np.testing.assert_array_equal(engine.topk(cu(big), 5000).cpu().numpy(), orc.topk_ascending(big, 5000))
+    assert engine.topk(cu(loss[:1]), 1).cpu().tolist() == [0]
+
+
+def test_modules_autograd_contract(small):
+    """SamplingLoss / BatchSamplingLoss keep the reference's signature and gradient flow."""
+    from piccolo_b200.omniloc import BatchSamplingLoss, SamplingLoss
+    xyz, rgb, img = cu(small["xyz"]), cu(small["rgb"]), cu(small["img"])
+    cfg = Cfg(4, 0.1, 100, 5, 0.9, 0.05)
+    p = cu(small["poses"][1])
+    t = p[:3].reshape(3, 1).clone().requires_grad_()
+    yaw, pitch, roll = [p[i:i + 1].clone().requires_grad_() for i in (3, 4, 5)]
+    loss = SamplingLoss(xyz, rgb, img, dev(), cfg)(t, yaw, pitch, roll)
+    assert loss.dim() == 0
+    loss.backward()
+    g = np.concatenate([t.grad.reshape(3).cpu().numpy(), yaw.grad.cpu().numpy(), pitch.grad.cpu().numpy(), roll.grad.cpu().numpy()])
+    assert abs(loss.item() - small["loss32"][1]) <= LOSS_RTOL * small["loss32"][1]
+    assert grad_gate(g, small["grad64"][1], small["grad32"][1])[0]
+    pb = cu(small["poses"][:4])
+    tb = pb[:, :3].unsqueeze(-1).clone().requires_grad_()
+    yb, pib, rb = [pb[:, i:i + 1].clone().requires_grad_() for i in (3, 4, 5)]
+    total, lst = BatchSamplingLoss(xyz, rgb, img, dev(), cfg)(tb, yb, pib, rb)
+    total.backward()
+    np.testing.assert_allclose(lst.detach().cpu().numpy(), small["batch_list"], rtol=LOSS_RTOL)
+    assert abs(total.item() - float(small["batch_total"])) <= LOSS_RTOL * float(small["batch_total"])
+    assert tb.grad.shape == (4, 3, 1) and yb.grad.shape == (4, 1)
+    for b in range(4):
+        gb = np.concatenate([tb.grad[b].reshape(3).cpu().numpy(), yb.grad[b].cpu().numpy(), pib.grad[b].cpu().numpy(), rb.grad[b].cpu().numpy()])
+        assert grad_gate(gb, small["grad64"][b], small["grad32"][b])[0], b
+
+
+@pytest.mark.parametrize("name", ["refine_small", "refine_medium"])
+def test_refinement_matches_reference(golden, name):
+    """omniloc / omniloc_batch: fused launch-per-iteration refinement vs the reference trajectories."""
+    from piccolo_b200.omniloc import omniloc, omniloc_batch
+    g = golden(name)
+    xyz, rgb, img = cu(g["xyz"]), cu(synth.rgb_from_u8(g["rgb8"])), cu(synth.img_from_u8(g["img8"]))
+    starts = cu(g["starts"])
+    cfg = Cfg(len(g["starts"]), 0.1, int(g["num_iter"]), 5, float(g["factor"]), 0.05)
+    lo, hi = orc.quantile_box_np(g["xyz"], 0.05)
+    for b in range(len(g["starts"])):
+        t, R, loss = omniloc(img, xyz, rgb, starts[:, :3], starts[:, 3:], b, cfg, None)
+        assert t.shape == (3, 1) and R.shape == (3, 3) and loss.dim() == 0 and t.device.type == "cpu"
+        t = t.numpy().reshape(3)
+        assert np.all(t >= lo) and np.all(t <= hi)
+        if g["seq_loss"][b] > 3 * g["seq_loss"].min():      # chaotic candidate stuck at the box corner
+            assert abs(loss.item() - g["seq_loss"][b]) <= 0.05 * g["seq_loss"][b]
+            continue
+        assert np.linalg.norm(t - g["seq_t"][b]) < 0.01, (b, t, g["seq_t"][b])
+        assert rot_err_deg(R.numpy(), g["seq_R"][b]) < 0.1
+        assert abs(loss.item() - g["seq_loss"][b]) <= 0.05 * g["seq_loss"][b]
+    t, R, loss = omniloc_batch(img, xyz, rgb, starts[:, :3], starts[:, 3:], cfg, None)
+    assert np.linalg.norm(t.numpy().reshape(3) - g["bat_t"]) < 0.01
+    assert rot_err_deg(R.numpy(), g["bat_R"]) < 0.1
+    assert abs(loss.item() - float(g["bat_loss"])) <= 0.05 * float(g["bat_loss"])
+
+
+def test_refiner_state_matches_oracle_first_iterations(golden):
+    """Adam / plateau / clamp arithmetic step by step (first iterations, before fp32 noise can amplify)."""
+    from piccolo_b200 import engine
+    g = golden("refine_small")
+    rgb, img = synth.rgb_from_u8(g["rgb8"]), synth.img_from_u8(g["img8"])
+    cloud = engine.Cloud(cu(g["xyz"]), cu(rgb))
+    image = engine.Image(cu(img))
+    for bs in (False, True):
+        ref = engine.Refiner(len(g["starts"]), 0.1, 0.8, 5, bs).reset(cu(g["starts"]))
+        o = orc.refine_np(g["xyz"], rgb, img, g["starts"], lr=0.1, num_iter=3, patience=5, factor=0.8, q=0.05,
+                          batch_semantics=bs, dtype=np.float32)
+        out = ref.run(cloud, image, 3).read()
+        np.testing.assert_allclose(out["pose"].cpu().numpy(), o["pose"], atol=2e-4)
+        np.testing.assert_allclose(out["param"].cpu().numpy(), o["param"], atol=2e-4)
+        np.testing.assert_allclose(out["loss"].cpu().numpy(), o["loss"], rtol=1e-3)
+    # the batch quirk: candidate 2 starts outside the box -> evaluated pose stays un-clamped, parameter is clamped
+    lo, hi = orc.quantile_box_np(g["xyz"], 0.05)
+    p = out["param"].cpu().numpy()[2, :3]
+    assert np.all(p >= lo) and np.all(p <= hi)
+
+
+def test_plateau_schedule_reduces_lr(golden):
+    from piccolo_b200 import engine
+    g = golden("refine_small")
+    rgb, img = synth.rgb_from_u8(g["rgb8"]), synth.img_from_u8(g["img8"])
+    cloud = engine.Cloud(cu(g["xyz"]), cu(rgb))
+    image = engine.Image(cu(img))
+    ref = engine.Refiner(3, 0.1, 0.8, 5, False).reset(cu(g["starts"]))
+    o = orc.refine_np(g["xyz"], rgb, img, g["starts"], lr=0.1, num_iter=30, patience=5, factor=0.8, q=0.05, dtype=np.float32)
+    lr = ref.run(cloud, image, 30).read()["lr"].cpu().numpy()
+    assert (lr <= 0.1).all() and (lr > 0).all()
+    # lr values are powers of the factor: 0.1 * 0.8^k
+    k = np.log(lr / 0.1) / np.log(0.8)
+    np.testing.assert_allclose(k, np.round(k), atol=1e-6)
+    np.testing.assert_allclose(lr[:2], o["lr"][:2], rtol=1e-9)
+
+
+def test_seeded_scene_vs_oracle_and_properties():
+    """Larger seeded scene: oracle parity on a pose subset + size-independent properties."""
+    from piccolo_b200 import engine
+    sc = synth.make_scene(200_000, 256, 512, seed=4)
+    xyz, rgb, img = sc.xyz, sc.rgb, sc.img
+    rng = np.random.default_rng(9)
+    poses = np.stack([sc.gt_pose + np.concatenate([rng.normal(0, 0.4, 3), rng.normal(0, 0.3, 3)]) for _ in range(40)]).astype(np.float32)
+    poses[0] = sc.gt_pose
+    cloud = engine.Cloud(cu(xyz), cu(rgb))
+    image = engine.Image(cu(img))
+    loss, count, grad = engine.loss_fwd_bwd(cloud, image, cu(poses))
+    loss_s, count_s = engine.score(cloud, image, cu(poses))
+    for i in (0, 1, 2, 3):
+        l64, m64, g64 = orc.loss_and_grad_np(xyz, rgb, img, poses[i].astype(np.float64), np.float64)
+        l32, m32, g32 = orc.loss_and_grad_np(xyz, rgb, img, poses[i], np.float32)
+        assert abs(loss[i].item() - l64) <= LOSS_RTOL * l64
+        assert abs(count[i].item() - m64) <= 2          # a point exactly on the black-cap boundary may flip
+        ok, err, tol = grad_gate(grad[i].cpu().numpy(), g64, g32)
+        assert ok, (i, err, tol)
+    # the ground-truth pose has the smallest loss
+    assert int(loss.argmin()) == 0
+    # determinism: bit-identical across launches
+    loss2, _, grad2 = engine.loss_fwd_bwd(cloud, image, cu(poses))
+    assert torch.equal(loss, loss2) and torch.equal(grad, grad2)
+    # additivity over a split of the cloud: Σ m·e and Σ m add up
+    half = len(xyz) // 2
+    ca, cb = engine.Cloud(cu(xyz[:half]), cu(rgb[:half])), engine.Cloud(cu(xyz[half:]), cu(rgb[half:]))
+    la, na = engine.score(ca, image, cu(poses))
+    lb, nb = engine.score(cb, image, cu(poses))
+    np.testing.assert_array_equal((na + nb).cpu().numpy(), count_s.cpu().numpy())
+    np.testing.assert_allclose(((la * na + lb * nb) / (na + nb)).cpu().numpy(), loss_s.cpu().numpy(), rtol=2e-6)
+    # permutation invariance (only the fp32 summation order changes)
+    perm = rng.permutation(len(xyz))
+    lp, _ = engine.score(engine.Cloud(cu(xyz[perm]), cu(rgb[perm]), 0.05, 0), image, cu(poses))
+    np.testing.assert_allclose(lp.cpu().numpy(), loss_s.cpu().numpy(), rtol=2e-6)
+
+
+def test_ragged_sizes():
+    """Cloud sizes around the tile padding boundary, tiny clouds, single pose, >32 poses."""
+    from piccolo_b200 import engine
+    sc = synth.make_scene(5000, 64, 128, seed=8)
+    image = engine.Image(cu(sc.img))
+    rng = np.random.default_rng(1)
+    poses = np.stack([sc.gt_pose + np.concatenate([rng.normal(0, 0.3, 3), rng.normal(0, 0.2, 3)]) for _ in range(70)]).astype(np.float32)
+    for n in (1, 31, 2047, 2048, 2049, 4097):
+        cloud = engine.Cloud(cu(sc.xyz[:n]), cu(sc.rgb[:n]))
+        loss, count = engine.score(cloud, image, cu(poses))
+        ref, cnt = orc.score_poses_np(sc.xyz[:n], sc.rgb[:n], sc.img, poses[:5], np.float32)
+        np.testing.assert_allclose(loss[:5].cpu().numpy(), ref, rtol=LOSS_RTOL, equal_nan=True)
+        np.testing.assert_array_equal(count[:5].cpu().numpy(), cnt)
+        l1, c1, g1 = engine.loss_fwd_bwd(cloud, image, cu(poses[:1]))
+        assert abs(l1.item() - ref[0]) <= LOSS_RTOL * abs(ref[0]) or (np.isnan(ref[0]) and torch.isnan(l1).all())
