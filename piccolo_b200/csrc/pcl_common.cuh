@@ -62,7 +62,7 @@ struct pcl_refine {
   double lr0, factor;
   PclRefineState* state;        // [B]
   float* evalp;                 // [B][6] pose evaluated by the next forward
-  float* partial;               // grow-only scratch for per-CTA partial sums
+  double* partial;              // grow-only scratch for per-CTA partial sums
   size_t partial_floats;
   unsigned int* counters;       // last-block-done tickets
   float* loss;                  // [B]

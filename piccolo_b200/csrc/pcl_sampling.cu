@@ -89,10 +89,10 @@ __device__ void pcl_refine_update(PclRefineState& st, float* evalp, const float*
 template <int FMT, bool BWD, int K>
 __global__ void __launch_bounds__(PCL_THREADS, BWD ? 2 : 3)
 pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, const int P, const int PB,
-                  const int n_tiles, float* __restrict__ partial, unsigned int* __restrict__ counters, const PclFinalize fin) {
+                  const int n_tiles, double* __restrict__ partial, unsigned int* __restrict__ counters, const PclFinalize fin) {
   constexpr int NS = BWD ? PCL_NSUM : 2;
   __shared__ __align__(16) PclPose s_pose[PCL_MAX_POSE_BLOCK];
-  __shared__ float s_acc[PCL_WARPS][PCL_MAX_POSE_BLOCK][NS];
+  __shared__ double s_acc[PCL_WARPS][PCL_MAX_POSE_BLOCK][NS];   // fp64: tile-to-tile accumulation adds no fp32 error
   __shared__ double s_sum[PCL_MAX_POSE_BLOCK][PCL_NSUM];
   __shared__ int s_last;
 
@@ -101,7 +101,7 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
   const int np = min(PB, P - p0);
 
   if (tid < np) pcl_pose_from_params(poses6 + 6 * (size_t)(p0 + tid), s_pose[tid]);
-  for (int i = tid; i < PCL_WARPS * PCL_MAX_POSE_BLOCK * NS; i += PCL_THREADS) (&s_acc[0][0][0])[i] = 0.0f;
+  for (int i = tid; i < PCL_WARPS * PCL_MAX_POSE_BLOCK * NS; i += PCL_THREADS) (&s_acc[0][0][0])[i] = 0.0;
   __syncthreads();
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -129,7 +129,7 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
       }
       if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < NS; ++s) s_acc[warp][p][s] += v[s];
+        for (int s = 0; s < NS; ++s) s_acc[warp][p][s] += (double)v[s];
       }
     }
   }
@@ -138,7 +138,7 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
   // CTA partial row: partial[blockIdx.x][s][pose]
   for (int i = tid; i < np * NS; i += PCL_THREADS) {
     const int s = i / np, p = i - s * np;
-    float t = 0.0f;
+    double t = 0.0;
 #pragma unroll
     for (int w = 0; w < PCL_WARPS; ++w) t += s_acc[w][p][s];
     partial[((size_t)blockIdx.x * NS + s) * (size_t)P + (size_t)(p0 + p)] = t;
@@ -159,7 +159,7 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
     const int s = i / np, p = i - s * np;
     double t = 0.0;
     for (unsigned int bx = 0; bx < gridDim.x; ++bx)
-      t += (double)__ldcg(partial + ((size_t)bx * NS + s) * (size_t)P + (size_t)(p0 + p));
+      t += __ldcg(partial + ((size_t)bx * NS + s) * (size_t)P + (size_t)(p0 + p));
     s_sum[p][s] = t;
   }
   __syncthreads();
@@ -223,7 +223,7 @@ static PclLaunchPlan pcl_plan(const pcl_cloud* c, int64_t P, bool bwd) {
 
 template <int FMT, bool BWD>
 static void pcl_launch_fmt(const PclLaunchPlan& pl, const PclCloudView& C, const PclImage& I, const float* poses, int P,
-                           float* partial, unsigned int* counters, const PclFinalize& fin, cudaStream_t st) {
+                           double* partial, unsigned int* counters, const PclFinalize& fin, cudaStream_t st) {
   dim3 grid(pl.gx, pl.gy), block(PCL_THREADS);
   switch (pl.K) {
     case 2: pcl_sample_kernel<FMT, BWD, 2><<<grid, block, 0, st>>>(C, I, poses, P, pl.PB, pl.n_tiles, partial, counters, fin); break;
@@ -234,7 +234,7 @@ static void pcl_launch_fmt(const PclLaunchPlan& pl, const PclCloudView& C, const
 
 template <bool BWD>
 static int pcl_launch(const PclLaunchPlan& pl, const pcl_cloud* c, const pcl_image* im, const float* poses, int P,
-                      float* partial, unsigned int* counters, const PclFinalize& fin, cudaStream_t st) {
+                      double* partial, unsigned int* counters, const PclFinalize& fin, cudaStream_t st) {
   PclCloudView C = {c->x, c->y, c->z, c->r, c->g, c->b, (long long)c->n};
   switch (im->view.fmt) {
     case PCL_FMT_U8Q: pcl_launch_fmt<PCL_FMT_U8Q, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st); break;
@@ -258,9 +258,9 @@ static int pcl_check_inputs(const pcl_cloud* c, const pcl_image* im, const void*
 static int pcl_run_once(const pcl_cloud* c, const pcl_image* im, const float* poses, int64_t P, bool bwd,
                         float* loss, float* count, float* grad, cudaStream_t st) {
   const PclLaunchPlan pl = pcl_plan(c, P, bwd);
-  float* partial = nullptr;
+  double* partial = nullptr;
   unsigned int* counters = nullptr;
-  const size_t pbytes = (size_t)pl.gx * pl.NS * (size_t)P * sizeof(float);
+  const size_t pbytes = (size_t)pl.gx * pl.NS * (size_t)P * sizeof(double);
   PCL_CUDA(cudaMallocAsync((void**)&partial, pbytes + (size_t)pl.gy * sizeof(unsigned int), st));
   counters = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(partial) + pbytes);
   PCL_CUDA(cudaMemsetAsync(counters, 0, (size_t)pl.gy * sizeof(unsigned int), st));
@@ -346,7 +346,7 @@ extern "C" int pcl_refine_run(pcl_refine* r, const pcl_cloud* c, const pcl_image
   const size_t need = (size_t)pl.gx * pl.NS * (size_t)r->B;
   if (need > r->partial_floats) {
     if (r->partial) { PCL_CUDA(cudaStreamSynchronize(st)); PCL_CUDA(cudaFree(r->partial)); }
-    PCL_CUDA(cudaMalloc((void**)&r->partial, need * sizeof(float)));
+    PCL_CUDA(cudaMalloc((void**)&r->partial, need * sizeof(double)));
     r->partial_floats = need;
   }
   PclFinalize fin;

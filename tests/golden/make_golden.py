@@ -111,30 +111,45 @@ def main():
     print("score_small: best", table.min(), "worst", table.max())
 
     # ---------------- fixture 3: refinement trajectories (omniloc / omniloc_batch) -------------
-    def run_refine(scn, starts, num_iter, tag, factor):
-        xyz_t, rgb_t, img_t = torch.from_numpy(scn.xyz), torch.from_numpy(scn.rgb), torch.from_numpy(scn.img)
-        st = torch.from_numpy(starts)
-        cfg = Cfg(len(starts), 0.1, num_iter, 5, factor, 0.05)
-        seq = [ref_omniloc.omniloc(img_t, xyz_t, rgb_t, st[:, :3].clone(), st[:, 3:].clone(), i, cfg, None) for i in range(len(starts))]
-        bat = ref_omniloc.omniloc_batch(img_t, xyz_t, rgb_t, st[:, :3].clone(), st[:, 3:].clone(), cfg, None)
+    def run_refine(scn, starts, num_iter, tag, factor, early_iter):
+        """omniloc per candidate + omniloc_batch in fp32 (the parity target), the same after `early_iter`
+        iterations (trajectories still correlated: tight gate), and in fp64 (the reference's own
+        fp32-vs-fp64 spread bounds how reproducible the end state is)."""
+        def run(dtype, n_it):
+            torch.set_default_dtype(dtype)
+            try:
+                xyz_t, rgb_t, img_t = [torch.from_numpy(a).to(dtype) for a in (scn.xyz, scn.rgb, scn.img)]
+                st = torch.from_numpy(starts).to(dtype)
+                cfg = Cfg(len(starts), 0.1, n_it, 5, factor, 0.05)
+                seq = [ref_omniloc.omniloc(img_t, xyz_t, rgb_t, st[:, :3].clone(), st[:, 3:].clone(), i, cfg, None) for i in range(len(starts))]
+                bat = ref_omniloc.omniloc_batch(img_t, xyz_t, rgb_t, st[:, :3].clone(), st[:, 3:].clone(), cfg, None)
+            finally:
+                torch.set_default_dtype(torch.float32)
+            return {"seq_t": np.stack([s[0].detach().numpy().reshape(3) for s in seq]),
+                    "seq_R": np.stack([s[1].detach().numpy() for s in seq]),
+                    "seq_loss": np.array([float(s[2]) for s in seq]),
+                    "bat_t": bat[0].detach().numpy().reshape(3), "bat_R": bat[1].detach().numpy(), "bat_loss": float(bat[2])}
         res = {"xyz": scn.xyz, "rgb8": scn.rgb8, "img8": scn.img8, "starts": starts, "gt_pose": scn.gt_pose,
-               "num_iter": num_iter, "factor": factor,
-               "seq_t": np.stack([s[0].detach().numpy().reshape(3) for s in seq]),
-               "seq_R": np.stack([s[1].detach().numpy() for s in seq]),
-               "seq_loss": np.array([float(s[2]) for s in seq], dtype=np.float32),
-               "bat_t": bat[0].detach().numpy().reshape(3), "bat_R": bat[1].detach().numpy(), "bat_loss": np.float32(float(bat[2]))}
+               "num_iter": num_iter, "factor": factor, "early_iter": early_iter}
+        full32, early32, full64 = run(torch.float32, num_iter), run(torch.float32, early_iter), run(torch.float64, num_iter)
+        for k, v in full32.items():
+            res[k] = np.asarray(v, dtype=np.float32)
+        for k, v in early32.items():
+            res["early_" + k] = np.asarray(v, dtype=np.float32)
+        for k, v in full64.items():
+            res["f64_" + k] = np.asarray(v, dtype=np.float64)
         np.savez_compressed(os.path.join(HERE, tag + ".npz"), **res)
         print(tag, "seq_loss", res["seq_loss"], "bat_loss", res["bat_loss"], "t", res["bat_t"], "gt", scn.gt_pose[:3])
 
     rng = np.random.default_rng(5)
     starts = np.stack([gt + np.concatenate([rng.normal(0, 0.25, 3), rng.normal(0, 0.15, 3)]) for _ in range(3)]).astype(np.float32)
     starts[2, :3] = [7.9, 0.2, 2.9]   # starts outside the 5-95 % box: exercises the clamp (and the batch quirk)
-    run_refine(sc, starts, 30, "refine_small", 0.8)
+    run_refine(sc, starts, 30, "refine_small", 0.8, 8)
 
     sc2 = synth.make_scene(50000, 256, 512, seed=3)
     rng = np.random.default_rng(6)
     starts2 = np.stack([sc2.gt_pose + np.concatenate([rng.normal(0, 0.2, 3), rng.normal(0, 0.12, 3)]) for _ in range(3)]).astype(np.float32)
-    run_refine(sc2, starts2, 100, "refine_medium", 0.8)
+    run_refine(sc2, starts2, 100, "refine_medium", 0.8, 20)
 
     # medium loss/grad vectors
     poses2 = np.concatenate([starts2, sc2.gt_pose[None].astype(np.float32)], axis=0)

@@ -1,0 +1,25 @@
+"""Shared gates for the refinement-trajectory parity tests (CPU oracle and GPU)."""
+import numpy as np
+
+
+def rot_err_deg(Ra, Rb):
+    c = (np.trace(np.asarray(Ra, dtype=np.float64).T @ np.asarray(Rb, dtype=np.float64)) - 1) / 2
+    return np.rad2deg(np.arccos(np.clip(c, -1, 1)))
+
+
+def final_pose_gates(g, b=None):
+    """(translation gate [m], rotation gate [deg]) for candidate b (None = the omniloc_batch result).
+
+    North star: 1 cm / 0.1 deg.  The reference's own end state is only reproducible to its fp32-vs-fp64
+    spread (Adam still jitters with lr≈0.017 after 100 iterations; measured spread up to 0.15 deg, stored
+    in the fixture as f64_*), so the rotation gate is max(0.1 deg, 1.5 x that spread)."""
+    if b is None:
+        spread_t = np.linalg.norm(g["bat_t"] - g["f64_bat_t"])
+        spread_r = rot_err_deg(g["bat_R"], g["f64_bat_R"])
+    else:
+        spread_t = np.linalg.norm(g["seq_t"][b] - g["f64_seq_t"][b])
+        spread_r = rot_err_deg(g["seq_R"][b], g["f64_seq_R"][b])
+    return max(0.01, 1.5 * spread_t), max(0.1, 1.5 * spread_r)
+
+
+EARLY_T, EARLY_R = 3e-3, 0.05      # after `early_iter` iterations trajectories are still correlated

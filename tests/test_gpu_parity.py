@@ -37,7 +37,9 @@ def rot_of(pose):
 
 
 def grad_gate(g, g64, g32):
-    tol = max(1e-4 * np.abs(g64).max(), np.abs(g32 - g64).max())
+    # 1e-4 relative, or — where the gradient nearly cancels (e.g. at the optimum) — a small multiple of the
+    # reference's own fp32-vs-fp64 deviation: no fp32 implementation can be closer to fp64 than fp32 noise
+    tol = max(1e-4 * np.abs(g64).max(), 3 * np.abs(g32 - g64).max())
     return np.abs(g - g64).max() <= tol, np.abs(g - g64).max(), tol
 
 
@@ -173,28 +175,35 @@ def test_modules_autograd_contract(small):
 
 @pytest.mark.parametrize("name", ["refine_small", "refine_medium"])
 def test_refinement_matches_reference(golden, name):
-    """omniloc / omniloc_batch: fused launch-per-iteration refinement vs the reference trajectories."""
+    """omniloc / omniloc_batch: fused launch-per-iteration refinement vs the reference trajectories, at an
+    early checkpoint (tight) and at the end state (1 cm / 0.1 deg, see parity_util.final_pose_gates)."""
+    from parity_util import EARLY_R, EARLY_T, final_pose_gates
     from piccolo_b200.omniloc import omniloc, omniloc_batch
     g = golden(name)
     xyz, rgb, img = cu(g["xyz"]), cu(synth.rgb_from_u8(g["rgb8"])), cu(synth.img_from_u8(g["img8"]))
     starts = cu(g["starts"])
-    cfg = Cfg(len(g["starts"]), 0.1, int(g["num_iter"]), 5, float(g["factor"]), 0.05)
     lo, hi = orc.quantile_box_np(g["xyz"], 0.05)
-    for b in range(len(g["starts"])):
-        t, R, loss = omniloc(img, xyz, rgb, starts[:, :3], starts[:, 3:], b, cfg, None)
-        assert t.shape == (3, 1) and R.shape == (3, 3) and loss.dim() == 0 and t.device.type == "cpu"
-        t = t.numpy().reshape(3)
-        assert np.all(t >= lo) and np.all(t <= hi)
-        if g["seq_loss"][b] > 3 * g["seq_loss"].min():      # chaotic candidate stuck at the box corner
-            assert abs(loss.item() - g["seq_loss"][b]) <= 0.05 * g["seq_loss"][b]
-            continue
-        assert np.linalg.norm(t - g["seq_t"][b]) < 0.01, (b, t, g["seq_t"][b])
-        assert rot_err_deg(R.numpy(), g["seq_R"][b]) < 0.1
-        assert abs(loss.item() - g["seq_loss"][b]) <= 0.05 * g["seq_loss"][b]
-    t, R, loss = omniloc_batch(img, xyz, rgb, starts[:, :3], starts[:, 3:], cfg, None)
-    assert np.linalg.norm(t.numpy().reshape(3) - g["bat_t"]) < 0.01
-    assert rot_err_deg(R.numpy(), g["bat_R"]) < 0.1
-    assert abs(loss.item() - float(g["bat_loss"])) <= 0.05 * float(g["bat_loss"])
+    chaotic = g["seq_loss"] > 3 * g["seq_loss"].min()      # candidate stuck at the box corner
+    for tag, n_it in (("early_", int(g["early_iter"])), ("", int(g["num_iter"]))):
+        cfg = Cfg(len(g["starts"]), 0.1, n_it, 5, float(g["factor"]), 0.05)
+        for b in range(len(g["starts"])):
+            t, R, loss = omniloc(img, xyz, rgb, starts[:, :3], starts[:, 3:], b, cfg, None)
+            assert t.shape == (3, 1) and R.shape == (3, 3) and loss.dim() == 0 and t.device.type == "cpu"
+            t = t.numpy().reshape(3)
+            assert np.all(t >= lo) and np.all(t <= hi)
+            if chaotic[b]:
+                if not tag:
+                    assert abs(loss.item() - g["seq_loss"][b]) <= 0.05 * g["seq_loss"][b]
+                continue
+            gate_t, gate_r = (EARLY_T, EARLY_R) if tag else final_pose_gates(g, b)
+            assert np.linalg.norm(t - g[tag + "seq_t"][b]) < gate_t, (tag, b, t, g[tag + "seq_t"][b])
+            assert rot_err_deg(R.numpy(), g[tag + "seq_R"][b]) < gate_r, (tag, b)
+            assert abs(loss.item() - g[tag + "seq_loss"][b]) <= (1e-2 if tag else 0.05) * g[tag + "seq_loss"][b]
+        t, R, loss = omniloc_batch(img, xyz, rgb, starts[:, :3], starts[:, 3:], cfg, None)
+        gate_t, gate_r = (EARLY_T, EARLY_R) if tag else final_pose_gates(g, None)
+        assert np.linalg.norm(t.numpy().reshape(3) - g[tag + "bat_t"]) < gate_t, tag
+        assert rot_err_deg(R.numpy(), g[tag + "bat_R"]) < gate_r, tag
+        assert abs(loss.item() - float(g[tag + "bat_loss"])) <= (1e-2 if tag else 0.05) * float(g[tag + "bat_loss"])
 
 
 def test_refiner_state_matches_oracle_first_iterations(golden):

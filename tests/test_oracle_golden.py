@@ -98,26 +98,41 @@ def test_topk_ties_and_nan():
 
 @pytest.mark.parametrize("name", ["refine_small", "refine_medium"])
 def test_refinement_trajectories(golden, name):
+    from parity_util import EARLY_R, EARLY_T, final_pose_gates
     g = golden(name)
     rgb, img = synth.rgb_from_u8(g["rgb8"]), synth.img_from_u8(g["img8"])
-    kw = dict(lr=0.1, num_iter=int(g["num_iter"]), patience=5, factor=float(g["factor"]), q=0.05)
-    seq = orc.refine_np(g["xyz"], rgb, img, g["starts"], batch_semantics=False, dtype=np.float32, **kw)
+    kw = dict(lr=0.1, patience=5, factor=float(g["factor"]), q=0.05)
     lo, hi = orc.quantile_box_np(g["xyz"], 0.05)
+    chaotic = g["seq_loss"] > 3 * g["seq_loss"].min()   # stuck at the box corner: fp32 noise is amplified
+    # early checkpoint: tight
+    seq = orc.refine_np(g["xyz"], rgb, img, g["starts"], num_iter=int(g["early_iter"]), batch_semantics=False, dtype=np.float32, **kw)
+    bat = orc.refine_np(g["xyz"], rgb, img, g["starts"], num_iter=int(g["early_iter"]), batch_semantics=True, dtype=np.float32, **kw)
+    for b in range(len(g["starts"])):
+        if chaotic[b]:
+            continue
+        assert np.linalg.norm(seq["pose"][b, :3] - g["early_seq_t"][b]) < EARLY_T, b
+        assert rot_err_deg(rot_of(seq["pose"][b]), g["early_seq_R"][b]) < EARLY_R, b
+        assert abs(seq["loss"][b] - g["early_seq_loss"][b]) <= 1e-2 * g["early_seq_loss"][b], b
+    k = int(np.argmin(bat["loss"]))
+    assert np.linalg.norm(bat["pose"][k, :3] - g["early_bat_t"]) < EARLY_T
+    assert rot_err_deg(rot_of(bat["pose"][k]), g["early_bat_R"]) < EARLY_R
+    # end state
+    seq = orc.refine_np(g["xyz"], rgb, img, g["starts"], num_iter=int(g["num_iter"]), batch_semantics=False, dtype=np.float32, **kw)
     for b in range(len(g["starts"])):
         assert np.all(seq["pose"][b, :3] >= lo) and np.all(seq["pose"][b, :3] <= hi)
-        if g["seq_loss"][b] > 3 * g["seq_loss"].min():
-            # a candidate stuck against the box corner follows a chaotic trajectory (fp32 noise is
-            # amplified): only the clamp and the loss level are comparable
+        if chaotic[b]:
             assert abs(seq["loss"][b] - g["seq_loss"][b]) <= 0.05 * g["seq_loss"][b], b
             continue
-        assert np.linalg.norm(seq["pose"][b, :3] - g["seq_t"][b]) < 0.01, b            # 1 cm
-        assert rot_err_deg(rot_of(seq["pose"][b]), g["seq_R"][b]) < 0.1, b             # 0.1 deg
+        gate_t, gate_r = final_pose_gates(g, b)
+        assert np.linalg.norm(seq["pose"][b, :3] - g["seq_t"][b]) < gate_t, b
+        assert rot_err_deg(rot_of(seq["pose"][b]), g["seq_R"][b]) < gate_r, b
         # the last-forward loss jitters with Adam's final steps; poses are the parity gate
         assert abs(seq["loss"][b] - g["seq_loss"][b]) <= 0.05 * g["seq_loss"][b], b
-    bat = orc.refine_np(g["xyz"], rgb, img, g["starts"], batch_semantics=True, dtype=np.float32, **kw)
+    bat = orc.refine_np(g["xyz"], rgb, img, g["starts"], num_iter=int(g["num_iter"]), batch_semantics=True, dtype=np.float32, **kw)
     k = int(np.argmin(bat["loss"]))
-    assert np.linalg.norm(bat["pose"][k, :3] - g["bat_t"]) < 0.01
-    assert rot_err_deg(rot_of(bat["pose"][k]), g["bat_R"]) < 0.1
+    gate_t, gate_r = final_pose_gates(g, None)
+    assert np.linalg.norm(bat["pose"][k, :3] - g["bat_t"]) < gate_t
+    assert rot_err_deg(rot_of(bat["pose"][k]), g["bat_R"]) < gate_r
     assert abs(bat["loss"][k] - g["bat_loss"]) <= 0.05 * g["bat_loss"]
 
 
