@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the sampling-loss pose search (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework on N B200s
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+A *step* is one localisation query of config C2 ("stanford_parallel.ini settings on a synthetic
+1M-point cloud, 1024x2048 panorama, all candidates refined in parallel"): forward-only scoring of the
+1 800-pose start grid (75 translations x 24 rotations, utils.py:462-507) -> top-K -> 100 fused
+forward+backward refinement iterations of the 6 surviving candidates with `omniloc_batch` semantics
+(omniloc.py:205-296) -> arg-min.  Metric: pose·point loss evaluations per second (whole job);
+`sec_per_query` is the step time.  N>1: one query per GPU per step (queries sharded),
+results all-gathered with NCCL; weak scaling.
+
+value  : inputs resident in HBM (packed cloud + texel table + grid), CUDA events per step, max over ranks.
+e2e    : the same query through the host-buffer entry (pinned host tensors in, pose out): H2D copies,
+         cloud packing (Morton sort + clamp box), texel-table build, query, D2H read — all timed.
+roofline: the fused forward+backward kernel: 24 B algorithmic bytes per pose·point evaluation
+         / its average launch duration (CUDA events on the launching stream), against the measured HBM peak.
+cpu_baseline: the oracle's ATen-chain port on the host cores, bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+ALGO_BYTES_PER_EVAL = 24.0   # one point = xyz 3xf32 + rgb 3xf32
+METRIC = "pose_point_loss_evals_per_sec"
+UNIT = "pose*point/s"
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def stanford_grid(sc, device):
+    """75 translations (5x5x3 lattice in the 10-90 % box) x 24 unique rotations of the 4x4x4 Euler lattice."""
+    from piccolo_b200 import synth
+    from piccolo_b200.utils import generate_rot_points, grid_poses
+    rot = generate_rot_points({"yaw_only": False, "num_yaw": 4, "num_pitch": 4, "num_roll": 4})
+    trans = torch.from_numpy(np.ascontiguousarray(synth.pose_grid(sc.room, (5, 5, 3), 1)[:, :3]))
+    return grid_poses(trans, rot).to(device)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_port_sample(sc, grid_cpu, cfg, n_score, n_iter, threads=None):
+    """Bounded sample of the workload on the host cores with the oracle's ATen-chain port
+    (the reference's own algorithm and third-party primitives): n_score grid poses forward-only through the
+    `trim_input_loss` loop + n_iter refinement iterations of the 6 candidates (Adam + plateau + clamp)."""
+    from oracle import piccolo_oracle as orc
+    if threads:
+        torch.set_num_threads(threads)
+    xyz, rgb, img = [torch.from_numpy(a) for a in (sc.xyz, sc.rgb, sc.img)]
+    n = xyz.shape[0]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for i in range(n_score):
+            orc.sampling_loss_torch(xyz, rgb, img, grid_cpu[i:i + 1])
+    t1 = time.perf_counter()
+    orc.refine_torch(xyz, rgb, img, grid_cpu[: cfg.num_input].clone(), lr=cfg.lr, num_iter=n_iter, patience=cfg.patience,
+                     factor=cfg.factor, q=cfg.out_of_room_quantile, batch_semantics=bool(cfg.parallel))
+    t2 = time.perf_counter()
+    evals = n * (n_score + n_iter * cfg.num_input)
+    return {"evals": evals, "seconds": t2 - t0, "score_s": t1 - t0, "refine_s": t2 - t1}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path (the oracle port; the reference is
+    pure Python and cannot travel to the GPU box) on the host cores, same config/metric/unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from piccolo_b200 import pipeline, synth
+    cfg = pipeline.STANFORD_PARALLEL
+    sc = synth.make_scene(args.n_points, args.height, 2 * args.height, seed=2)
+    grid = stanford_grid(sc, "cpu")
+    n_score, n_iter = 12, 1
+    for _ in range(args.warmup):
+        cpu_port_sample(sc, grid, cfg, 2, 1)
+    tot_e, tot_s = 0, 0.0
+    for _ in range(args.steps):
+        r = cpu_port_sample(sc, grid, cfg, n_score, n_iter)
+        tot_e += r["evals"]; tot_s += r["seconds"]
+    value = tot_e / tot_s
+    q_evals = pipeline.query_evals(args.n_points, grid.shape[0], cfg)
+    sample = f"per step: {n_score} of {grid.shape[0]} grid poses forward-only + {n_iter} of {cfg.num_iter} refinement iterations (B={cfg.num_input}), N={args.n_points}, {args.height}x{2*args.height}"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, grid.shape[0], cfg),
+            "sec_per_query_extrapolated": q_evals / value,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, n_grid, cfg):
+    return {"workload": "C2: stanford_parallel.ini settings, synthetic textured room", "n_points": args.n_points,
+            "panorama": f"{args.height}x{2*args.height}", "grid_poses": int(n_grid), "num_input": cfg.num_input, "num_iter": cfg.num_iter,
+            "refine_semantics": "omniloc_batch", "queries_per_gpu_per_step": 1,
+            "l2": "flushed between steps (256 MiB write); inputs (58 MB) are smaller than L2"}
+
+
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from piccolo_b200 import _lib, dist as pdist, engine, pipeline, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: piccolo_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if ws > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _lib.load()
+    cfg = pipeline.STANFORD_PARALLEL
+
+    # one cloud per room (replicated), one query panorama per rank
+    sc = synth.make_scene(args.n_points, args.height, 2 * args.height, seed=2)
+    if rank > 0:
+        gt = synth.random_gt_pose(sc.room, seed=2 + rank)
+        sc = synth.Scene(sc.xyz, sc.rgb8, synth.render_panorama(gt, args.height, 2 * args.height, sc.room), gt, sc.room)
+    grid = stanford_grid(sc, device)
+    P = grid.shape[0]
+    xyz_h, rgb_h, img_h, grid_h = [torch.from_numpy(a).pin_memory() for a in (sc.xyz, sc.rgb, sc.img)] + [grid.cpu().pin_memory()]
+    xyz, rgb, img = xyz_h.to(device), rgb_h.to(device), img_h.to(device)
+    cloud = engine.Cloud(xyz, rgb, cfg.out_of_room_quantile)
+    image = engine.Image(img)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    q_evals = pipeline.query_evals(args.n_points, P, cfg)
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps ------------------------------------------------------------------
+    names = ["step0", "score0", "score1", "refine0", "refine1", "step1"]
+    result = None
+    for _ in range(args.warmup):
+        result = pipeline.localize_query(cloud, image, grid, cfg)
+        if ws > 1:
+            pdist.gather_results(torch.cat([result["pose"], result["loss"].reshape(1)]))
+    evs = [{n: torch.cuda.Event(enable_timing=True) for n in names} for _ in range(args.steps)]
+    clock = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clock.start()
+    l0 = _lib.launch_count()
+    t_wall = time.perf_counter()
+    for s in range(args.steps):
+        flush.zero_()                                   # L2 flush between timed iterations (not timed)
+        evs[s]["step0"].record()
+        result = pipeline.localize_query(cloud, image, grid, cfg, timers=evs[s])
+        if ws > 1:
+            rows = pdist.gather_results(torch.cat([result["pose"], result["loss"].reshape(1)]))
+        evs[s]["step1"].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = _lib.launch_count() - l0
+    clocks = clock.stop() if rank == 0 else None
+    step_ms = [e["step0"].elapsed_time(e["step1"]) for e in evs]
+    score_ms = [e["score0"].elapsed_time(e["score1"]) for e in evs]
+    refine_ms = [e["refine0"].elapsed_time(e["refine1"]) for e in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
+    if ws > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = ws * q_evals * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host-buffer entry -------------------------------------------------
+    for _ in range(min(2, args.warmup)):
+        pipeline.localize_query_host(xyz_h, rgb_h, img_h, grid_h, cfg, device)
+    e2e_steps = max(1, min(args.steps, 5))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        pose_h, loss_h = pipeline.localize_query_host(xyz_h, rgb_h, img_h, grid_h, cfg, device)
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if ws > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms.item())
+    e2e_value = ws * q_evals * e2e_steps / (e2e_ms * 1e-3)
+    h2d = int(xyz_h.numel() * 4 + rgb_h.numel() * 4 + img_h.numel() * 4 + grid_h.numel() * 4)
+
+    if rank == 0:
+        peak, peak_kind = measured_hbm_peak()
+        bwd_launch_s = (sum(refine_ms) / len(refine_ms)) * 1e-3 / cfg.num_iter
+        bwd_achieved = ALGO_BYTES_PER_EVAL * cfg.num_input * args.n_points / bwd_launch_s / 1e9
+        sc_launch_s = (sum(score_ms) / len(score_ms)) * 1e-3
+        sc_achieved = ALGO_BYTES_PER_EVAL * P * args.n_points / sc_launch_s / 1e9
+        pose = result["pose"].cpu().numpy().astype(np.float64)
+        Rg, Rf = synth.rot_zyx(*sc.gt_pose[3:]), synth.rot_zyx(*pose[3:])
+        r_err = float(np.rad2deg(np.arccos(np.clip((np.trace(Rf.T @ Rg) - 1) / 2, -1, 1))))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, P, cfg),
+            "sec_per_query": total_ms / args.steps * 1e-3,
+            "phases_ms": {"score": sum(score_ms) / len(score_ms), "refine": sum(refine_ms) / len(refine_ms)},
+            "roofline": {"kernel": "pcl_sample_kernel<fmt,BWD=1> (fused fwd+bwd+reduce+Adam+plateau+clamp, one launch per iteration)",
+                         "bound": "hbm", "achieved": bwd_achieved, "peak": peak, "unit": "GB/s", "frac": bwd_achieved / peak, "traffic": None,
+                         "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_EVAL * cfg.num_input * args.n_points,
+                         "launch_us": bwd_launch_s * 1e6, "evals_per_s": cfg.num_input * args.n_points / bwd_launch_s},
+            "roofline_score": {"kernel": "pcl_sample_kernel<fmt,BWD=0> (forward-only grid scoring)", "bound": "hbm", "achieved": sc_achieved, "peak": peak,
+                               "unit": "GB/s", "frac": sc_achieved / peak, "traffic": None, "launch_us": sc_launch_s * 1e6,
+                               "evals_per_s": P * args.n_points / sc_launch_s},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 28, "sec_per_query": e2e_ms / e2e_steps * 1e-3,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
+            "result": {"t_error_m": float(np.linalg.norm(pose[:3] - sc.gt_pose[:3])), "r_error_deg": r_err, "loss": float(result["loss"].item())},
+        }
+        if ws == 1 and not args.no_cpu_baseline:
+            r = cpu_port_sample(sc, grid.cpu(), cfg, 24, 2)
+            line["cpu_baseline"] = {"value": r["evals"] / r["seconds"], "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"24 of {P} grid poses forward-only ({r['score_s']:.1f} s) + 2 of {cfg.num_iter} refinement iterations B={cfg.num_input} "
+                                              f"({r['refine_s']:.1f} s) of the same workload, oracle ATen-chain port, {torch.get_num_threads()} threads",
+                                    "sec_per_query_extrapolated": q_evals / (r["evals"] / r["seconds"])}
+        print(json.dumps(line))
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-points", type=int, default=1_000_000)
+    ap.add_argument("--height", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        ws = int(os.environ.get("WORLD_SIZE", "1"))
+        if ws != args.gpus and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={ws})")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -48,10 +48,12 @@ typedef enum pcl_status {
 } pcl_status;
 
 /* texel formats of a pcl_image */
-#define PCL_IMAGE_AUTO 0   /* u8 quad table if every value is k/255 exactly, else f32 */
+#define PCL_IMAGE_AUTO 0   /* image exactly k/255: F16D while the table fits L2 (<= 96 MB), else TEX; otherwise F32 */
 #define PCL_IMAGE_U8Q 1    /* 16-byte footprint entries {nw,ne,sw,se} RGBA8: one 128-bit load per sample */
 #define PCL_IMAGE_F32 2    /* fp32 RGBA texels: arbitrary float images */
 #define PCL_IMAGE_U8P 3    /* plain RGBA8 texels (4 B/texel): smallest table, four 32-bit loads */
+#define PCL_IMAGE_TEX 4    /* RGBA8 cudaArray behind a texture object: three 2x2 gathers per sample */
+#define PCL_IMAGE_F16D 5   /* 32-byte footprint entries of fp16 bilinear-basis values: two 128-bit loads, no unpack arithmetic */
 
 /* point ordering of a pcl_cloud */
 #define PCL_CLOUD_KEEP_ORDER 0

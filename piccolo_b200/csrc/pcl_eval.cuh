@@ -11,6 +11,10 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
 
 #if defined(__CUDACC__)
 #define PCL_HD __host__ __device__ __forceinline__
@@ -22,7 +26,7 @@
 #define PCL_HALF_PI_F 1.57079632679489661923f
 
 // image formats
-enum { PCL_FMT_AUTO = 0, PCL_FMT_U8Q = 1, PCL_FMT_F32 = 2, PCL_FMT_U8P = 3 };
+enum { PCL_FMT_AUTO = 0, PCL_FMT_U8Q = 1, PCL_FMT_F32 = 2, PCL_FMT_U8P = 3, PCL_FMT_TEX = 4, PCL_FMT_F16D = 5 };
 
 struct PclPose {          // R row-major, then t   (48 bytes, 16-byte aligned for LDS.128)
   float r00, r01, r02, r10;
@@ -35,25 +39,35 @@ struct PclImage {
   int H, W;
   int pitch;              // entries per row of the padded table
   int fmt;
-  float kx, cx;           // ix = cx - phi * kx      (phi = atan2(qy, qx+1e-6) in (-pi, pi])
-  float ky, cy;           // iy = theta * ky + cy    (theta = atan2(rho, qz+1e-6) in [0, pi])
+  float kx, cx;           // ix = cx - phi*kx      (phi = atan2(qy, qx+1e-6) in (-pi, pi])
+  float ky, cy;           // iy = theta*ky + cy    (theta = atan2(rho, qz+1e-6) in [0, pi])
+  float kxy;              // -kx / ky  (backward: the common factor ky is applied after the reduction)
   float ix_lo, ix_hi, iy_lo, iy_hi;   // the ±0.99 clip expressed in pixel coordinates
   float tex_scale;        // multiplies a blended texel to bring it to [0,1] (1/255 for u8 formats)
+  unsigned int idx_bias;  // see pcl_image_set_geometry
+  unsigned long long tex; // cudaTextureObject_t (PCL_FMT_TEX only)
 };
+
+#define PCL_MAGIC_F 12582912.0f      // 1.5 * 2^23: (x + MAGIC) rounded DOWN leaves MAGIC_I + floor(x) in the mantissa
+#define PCL_MAGIC_I 0x4B400000u
 
 // Geometry constants of an H×W panorama (host side; fp32 chain of grid_sampler_unnormalize for the
 // clip bounds so that clipped points land on exactly the reference's pixel coordinate).
-inline void pcl_image_set_geometry(PclImage& I, int H, int W) {
-  I.H = H; I.W = W;
+inline void pcl_image_set_geometry(PclImage& I, int H, int W, int pitch) {
+  I.H = H; I.W = W; I.pitch = pitch;
   I.kx = (float)((double)W / (2.0 * 3.14159265358979323846));
-  I.cx = 0.5f * (float)W - 0.5f;
+  I.cx = 0.5f * (float)W - 0.5f;                     // ix = W/2 - 0.5 - phi*W/(2 pi)
   I.ky = (float)((double)H / 3.14159265358979323846);
-  I.cy = -0.5f;
+  I.cy = -0.5f;                                      // iy = theta*H/pi - 0.5
+  I.kxy = -I.kx / I.ky;
   const float c = 0.99f;
   I.ix_hi = ((c + 1.0f) * (float)W - 1.0f) / 2.0f;
   I.ix_lo = ((-c + 1.0f) * (float)W - 1.0f) / 2.0f;
   I.iy_hi = ((c + 1.0f) * (float)H - 1.0f) / 2.0f;
   I.iy_lo = ((-c + 1.0f) * (float)H - 1.0f) / 2.0f;
+  // footprint (x0,y0) lives at table entry (y0+1)*pitch + (x0+1); the kernel has the integers
+  // MAGIC_I + x0 and MAGIC_I + y0 (mantissa of the magic add), so entry = yi*pitch + xi - bias (mod 2^32)
+  I.idx_bias = PCL_MAGIC_I * (unsigned int)pitch + PCL_MAGIC_I - (unsigned int)pitch - 1u;
 }
 
 struct PclAcc {           // per-pose running sums
@@ -77,6 +91,22 @@ PCL_HD float pcl_rsqrt(float x) {
   float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
 #else
   return 1.0f / sqrtf(x);
+#endif
+}
+
+// MAGIC + floor(x) for |x| < 2^22: one FADD with round-toward-minus-infinity
+PCL_HD float pcl_floor_magic(float x) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rd(x, PCL_MAGIC_F);
+#else
+  return PCL_MAGIC_F + floorf(x);
+#endif
+}
+PCL_HD float pcl_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return sqrtf(x);
 #endif
 }
 
@@ -120,15 +150,19 @@ PCL_HD float pcl_atan2_pos(float y, float x) {
 // x0 in [-1, W-1], y0 in [-1, H-1]; out-of-image taps read the zero border baked into the table.
 // Values are in "table units" (0..255 for the u8 formats, 0..1 for f32).
 // ---------------------------------------------------------------------------------------------
+// Taps come back BIASED: u8 formats return 2^23 + byte (one PRMT each, exact); differences of biased taps
+// are exact byte differences, only the north-west tap is un-biased (one FADD per channel).
 struct PclTaps { float nw[3], ne[3], sw[3], se[3]; };
 
-PCL_HD float pcl_u8_to_float(uint32_t w, int byte) {
+template <int FMT> struct PclTapBias { static constexpr float value = 8388608.0f; };
+template <> struct PclTapBias<PCL_FMT_F32> { static constexpr float value = 0.0f; };
+template <> struct PclTapBias<PCL_FMT_TEX> { static constexpr float value = 0.0f; };
+
+PCL_HD float pcl_u8_biased(uint32_t w, int byte) {
 #if defined(__CUDA_ARCH__)
-  // place the byte in the low mantissa of 2^23, then subtract 2^23: PRMT + FADD, exact
-  const uint32_t sel = 0x7650u + (uint32_t)byte;
-  return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f;
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + (uint32_t)byte));   // 2^23 + byte
 #else
-  return (float)((w >> (8 * byte)) & 0xffu);
+  return 8388608.0f + (float)((w >> (8 * byte)) & 0xffu);
 #endif
 }
 
@@ -149,35 +183,45 @@ struct pcl_f4 { float x, y, z, w; };
 #define PCL_LDGF4(p) (*reinterpret_cast<const pcl_f4*>(p))
 #endif
 
+// idx = table entry of the footprint's north-west texel (32-bit; tables have < 2^32 entries)
 template <int FMT>
-PCL_HD void pcl_fetch(const PclImage& I, int x0, int y0, PclTaps& t) {
-  if (FMT == PCL_FMT_U8Q) {
-    // one 16-byte entry per footprint: {nw, ne, sw, se} as RGBA8
-    const pcl_u4* tab = reinterpret_cast<const pcl_u4*>(I.data);
-    const pcl_u4 e = PCL_LDG128(tab + ((size_t)(y0 + 1) * (size_t)I.pitch + (size_t)(x0 + 1)));
+PCL_HD void pcl_fetch(const PclImage& I, unsigned int idx, float x0f, float y0f, PclTaps& t) {
+  if (FMT == PCL_FMT_TEX) {
+#if defined(__CUDA_ARCH__)
+    // RGBA8 block-linear cudaArray read through the texture unit: three 2x2 gathers (one per channel)
+    // return the four taps already converted to float (byte/255); no address math, no unpacking.
+    // Gather at the footprint centre (x0+1, y0+1) selects texels x0..x0+1, y0..y0+1; border mode gives 0.
+    const float gx = x0f + 1.0f, gy = y0f + 1.0f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      t.nw[c] = pcl_u8_to_float(e.x, c);
-      t.ne[c] = pcl_u8_to_float(e.y, c);
-      t.sw[c] = pcl_u8_to_float(e.z, c);
-      t.se[c] = pcl_u8_to_float(e.w, c);
+      const float4 g4 = tex2Dgather<float4>((cudaTextureObject_t)I.tex, gx, gy, c);   // .w nw  .z ne  .x sw  .y se
+      t.nw[c] = g4.w; t.ne[c] = g4.z; t.sw[c] = g4.x; t.se[c] = g4.y;
+    }
+#endif
+  } else if (FMT == PCL_FMT_U8Q) {
+    // one 16-byte entry per footprint: {nw, ne, sw, se} as RGBA8
+    const pcl_u4 e = PCL_LDG128(reinterpret_cast<const pcl_u4*>(I.data) + idx);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      t.nw[c] = pcl_u8_biased(e.x, c);
+      t.ne[c] = pcl_u8_biased(e.y, c);
+      t.sw[c] = pcl_u8_biased(e.z, c);
+      t.se[c] = pcl_u8_biased(e.w, c);
     }
   } else if (FMT == PCL_FMT_U8P) {
     // plain RGBA8 texels with a 1-texel zero border: 4 B per texel, four 32-bit loads
-    const uint32_t* tab = reinterpret_cast<const uint32_t*>(I.data);
-    const uint32_t* p = tab + ((size_t)(y0 + 1) * (size_t)I.pitch + (size_t)(x0 + 1));
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(I.data) + idx;
     const uint32_t a = PCL_LDG32(p), b = PCL_LDG32(p + 1), c2 = PCL_LDG32(p + I.pitch), d = PCL_LDG32(p + I.pitch + 1);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      t.nw[c] = pcl_u8_to_float(a, c);
-      t.ne[c] = pcl_u8_to_float(b, c);
-      t.sw[c] = pcl_u8_to_float(c2, c);
-      t.se[c] = pcl_u8_to_float(d, c);
+      t.nw[c] = pcl_u8_biased(a, c);
+      t.ne[c] = pcl_u8_biased(b, c);
+      t.sw[c] = pcl_u8_biased(c2, c);
+      t.se[c] = pcl_u8_biased(d, c);
     }
   } else {
     // fp32 RGBA texels with a 1-texel zero border: 16 B per texel, four 128-bit loads
-    const pcl_f4* tab = reinterpret_cast<const pcl_f4*>(I.data);
-    const pcl_f4* p = tab + ((size_t)(y0 + 1) * (size_t)I.pitch + (size_t)(x0 + 1));
+    const pcl_f4* p = reinterpret_cast<const pcl_f4*>(I.data) + idx;
     const pcl_f4 a = PCL_LDGF4(p), b = PCL_LDGF4(p + 1), c2 = PCL_LDGF4(p + I.pitch), d = PCL_LDGF4(p + I.pitch + 1);
     t.nw[0] = a.x; t.nw[1] = a.y; t.nw[2] = a.z;
     t.ne[0] = b.x; t.ne[1] = b.y; t.ne[2] = b.z;
@@ -186,12 +230,57 @@ PCL_HD void pcl_fetch(const PclImage& I, int x0, int y0, PclTaps& t) {
   }
 }
 
+// Bilinear basis of a footprint: s(fx, fy) = nw + fx·dxt + fy·(dy0 + fx·ddx)
+//   dxt = ne - nw, dy0 = sw - nw, ddx = (se - sw) - (ne - nw);   ds/dfx = dxt + fy·ddx, ds/dfy = dy0 + fx·ddx
+struct PclBasis { float nw[3], dxt[3], dy0[3], ddx[3]; };
+
+// fp16 <-> fp32 for the F16D table (values are integers in [-510, 510]: exact in fp16)
+PCL_HD float pcl_half_lo(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+  return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu)));
+#else
+  const uint32_t h = w & 0xffffu, sgn = (h & 0x8000u) << 16, ex = (h >> 10) & 0x1fu, man = h & 0x3ffu;
+  if (ex == 0 && man == 0) { float f; uint32_t b = sgn; memcpy(&f, &b, 4); return f; }
+  uint32_t b = sgn | ((ex + 112u) << 23) | (man << 13); float f; memcpy(&f, &b, 4); return f;   // normals only
+#endif
+}
+PCL_HD float pcl_half_hi(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+  return __half2float(__ushort_as_half((unsigned short)(w >> 16)));
+#else
+  return pcl_half_lo(w >> 16);
+#endif
+}
+
+template <int FMT>
+PCL_HD void pcl_fetch_basis(const PclImage& I, unsigned int idx, float x0f, float y0f, PclBasis& b) {
+  if (FMT == PCL_FMT_F16D) {
+    // 32-byte entry per footprint: for each channel the four basis values as fp16 (exact small integers):
+    // two 128-bit loads from one 32-byte sector, one conversion per value, no differences to form
+    const pcl_u4* e = reinterpret_cast<const pcl_u4*>(I.data) + 2 * (size_t)idx;
+    const pcl_u4 lo = PCL_LDG128(e), hi = PCL_LDG128(e + 1);
+    b.nw[0] = pcl_half_lo(lo.x); b.dxt[0] = pcl_half_hi(lo.x); b.dy0[0] = pcl_half_lo(lo.y); b.ddx[0] = pcl_half_hi(lo.y);
+    b.nw[1] = pcl_half_lo(lo.z); b.dxt[1] = pcl_half_hi(lo.z); b.dy0[1] = pcl_half_lo(lo.w); b.ddx[1] = pcl_half_hi(lo.w);
+    b.nw[2] = pcl_half_lo(hi.x); b.dxt[2] = pcl_half_hi(hi.x); b.dy0[2] = pcl_half_lo(hi.y); b.ddx[2] = pcl_half_hi(hi.y);
+  } else {
+    PclTaps t;
+    pcl_fetch<FMT>(I, idx, x0f, y0f, t);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      b.nw[c] = t.nw[c] - PclTapBias<FMT>::value;          // the only un-biasing
+      b.dxt[c] = t.ne[c] - t.nw[c];                        // exact differences of biased taps
+      b.dy0[c] = t.sw[c] - t.nw[c];
+      b.ddx[c] = (t.se[c] - t.sw[c]) - b.dxt[c];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // one pose·point evaluation
 // ---------------------------------------------------------------------------------------------
 template <int FMT, bool BWD>
 PCL_HD void pcl_eval(const PclPose& P, const PclImage& I, float px, float py, float pz,
-                     float cr, float cg, float cb, bool valid, PclAcc& acc) {
+                     float cr, float cg, float cb, bool valid, PclAcc& acc) {   // valid: false for padding points
   // q = R (p - t)
   const float dx = px - P.tx, dy = py - P.ty, dz = pz - P.tz;
   const float qx = fmaf(P.r02, dz, fmaf(P.r01, dy, P.r00 * dx));
@@ -199,42 +288,47 @@ PCL_HD void pcl_eval(const PclPose& P, const PclImage& I, float px, float py, fl
   const float qz = fmaf(P.r22, dz, fmaf(P.r21, dy, P.r20 * dx));
   const float xp = qx + 1e-6f, zp = qz + 1e-6f;
   const float rho2 = fmaf(qx, qx, qy * qy);
-  const float rinv = pcl_rsqrt(fmaxf(rho2, 1e-37f));
-  const float rho = rho2 * rinv;
+  float rinv = 0.0f, rho;
+  if (BWD) { rinv = pcl_rsqrt(fmaxf(rho2, 1e-37f)); rho = rho2 * rinv; } else { rho = pcl_sqrt(rho2); }
 
   const float phi = pcl_atan2(qy, xp);
   const float theta = pcl_atan2_pos(rho, zp);
+  // pixel coordinates, clipped; floor by a round-down magic add (mantissa = MAGIC_I + floor)
   const float ix_raw = fmaf(-phi, I.kx, I.cx);
   const float iy_raw = fmaf(theta, I.ky, I.cy);
   const float ix = fminf(fmaxf(ix_raw, I.ix_lo), I.ix_hi);
   const float iy = fminf(fmaxf(iy_raw, I.iy_lo), I.iy_hi);
-  const float fx0 = floorf(ix), fy0 = floorf(iy);
-  const float fx = ix - fx0, fy = iy - fy0;
+  const float tx = pcl_floor_magic(ix), ty = pcl_floor_magic(iy);
+  const float fx = ix - (tx - PCL_MAGIC_F);                               // exact fractional parts
+  const float fy = iy - (ty - PCL_MAGIC_F);
+#if defined(__CUDA_ARCH__)
+  const unsigned int xi = __float_as_uint(tx), yi = __float_as_uint(ty);
+#else
+  unsigned int xi, yi; { float a = tx, b = ty; memcpy(&xi, &a, 4); memcpy(&yi, &b, 4); }
+#endif
+  const unsigned int idx = yi * (unsigned int)I.pitch + xi - I.idx_bias;
 
-  PclTaps t;
-  pcl_fetch<FMT>(I, (int)fx0, (int)fy0, t);
+  PclBasis b;
+  pcl_fetch_basis<FMT>(I, idx, tx - PCL_MAGIC_F, ty - PCL_MAGIC_F, b);
 
-  float d[3], dsdx[3], dsdy[3], ssum = 0.0f;
+  float d[3], dsdx[3], dsdy[3], ssum = -0.0f;   // -0.0f + x == x exactly: the first add folds away
   const float col[3] = {cr, cg, cb};
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float dxt = t.ne[c] - t.nw[c];
-    const float dxb = t.se[c] - t.sw[c];
-    const float top = fmaf(fx, dxt, t.nw[c]);
-    const float bot = fmaf(fx, dxb, t.sw[c]);
-    const float dyv = bot - top;
+    const float top = fmaf(fx, b.dxt[c], b.nw[c]);
+    const float dyv = fmaf(fx, b.ddx[c], b.dy0[c]);        // bottom - top
     const float s = fmaf(fy, dyv, top);
     ssum += s;
     d[c] = fmaf(s, I.tex_scale, -col[c]);
     if (BWD) {
-      dsdx[c] = fmaf(fy, dxb - dxt, dxt);
+      dsdx[c] = fmaf(fy, b.ddx[c], b.dxt[c]);
       dsdy[c] = dyv;
     }
   }
   const bool m = valid && (ssum > 0.0f);      // texels are >= 0, so Σ == 0  <=>  all three are 0
   const float e2 = fmaf(d[2], d[2], fmaf(d[1], d[1], d[0] * d[0]));
-  const float einv = pcl_rsqrt(fmaxf(e2, 1e-37f));
-  const float e = e2 * einv;
+  float einv = 0.0f, e;
+  if (BWD) { einv = pcl_rsqrt(fmaxf(e2, 1e-37f)); e = e2 * einv; } else { e = pcl_sqrt(e2); }
   acc.se += m ? e : 0.0f;
   acc.sm += m ? 1.0f : 0.0f;
 
@@ -248,20 +342,23 @@ PCL_HD void pcl_eval(const PclPose& P, const PclImage& I, float px, float py, fl
     giy = (iy_raw == iy) ? giy : 0.0f;
     const float dphi = fmaf(xp, xp, qy * qy);
     const float dth = fmaf(zp, zp, rho2);
-    const float rr = pcl_rcp(fmaxf(dphi * dth, 1e-37f));
+    // one reciprocal for both denominators.  (dphi or dth == 0 needs qx == -1e-6 exactly; the reference's
+    // atan2 backward is 0/0 there as well.)
+    const float rr = pcl_rcp(dphi * dth);
     // ix = cx - kx·phi, iy = ky·theta + cy   =>   g_phi = -kx·g_ix, g_theta = ky·g_iy
     // phi = atan2(qy, xp):   dphi/dqx = -qy/dphi, dphi/dqy = xp/dphi
     // theta = atan2(rho, zp): dtheta/drho = zp/dth, dtheta/dzp = -rho/dth ; drho/dq{x,y} = q{x,y}/rho
-    const float A = (-I.kx * gix) * (rr * dth);         // g_phi / (xp² + qy²)
-    const float B = (I.ky * giy) * (rr * dphi);         // g_theta / (rho² + zp²)
+    // Everything is accumulated DIVIDED BY ky (kxy = -kx/ky); ky is applied once in pcl_finish_gradient.
+    const float A = (I.kxy * gix) * (rr * dth);         // g_phi / (xp² + qy²) / ky
+    const float B = giy * (rr * dphi);                  // g_theta / (rho² + zp²) / ky
     const float Bz = B * zp * rinv;                     // rho == 0  ->  multiplied by qx = qy = 0 below
     const float gqx = fmaf(Bz, qx, -A * qy);
     const float gqy = fmaf(Bz, qy, A * xp);
     const float gqz = -B * rho;
     acc.ax += gqx; acc.ay += gqy; acc.az += gqz;
-    acc.tx += fmaf(qy, gqz, -qz * gqy);
-    acc.ty += fmaf(qz, gqx, -qx * gqz);
-    acc.tz += fmaf(qx, gqy, -qy * gqx);
+    acc.tx = fmaf(qy, gqz, fmaf(-qz, gqy, acc.tx));     // τ += q × g_q
+    acc.ty = fmaf(qz, gqx, fmaf(-qx, gqz, acc.ty));
+    acc.tz = fmaf(qx, gqy, fmaf(-qy, gqx, acc.tz));
   }
 }
 
@@ -289,7 +386,7 @@ PCL_HD void pcl_finish_gradient(const float* p6, const PclPose& P, const PclImag
   *loss = (float)(sums[0] / M);               // 0/0 -> NaN, the reference's empty mean
   if (count) *count = (float)M;
   if (!grad6) return;
-  const double k = (double)I.tex_scale / M;   // g_s carries tex_scale (sample is s·tex_scale)
+  const double k = (double)I.tex_scale * (double)I.ky / M;   // g_s carries tex_scale; sums were accumulated / ky
   const double ax = sums[2] * k, ay = sums[3] * k, az = sums[4] * k;
   const double tx = sums[5] * k, ty = sums[6] * k, tz = sums[7] * k;
   // dL/dt = -Rᵀ a

@@ -38,10 +38,34 @@ extern "C" int64_t pcl_launch_count(void) { return (int64_t)g_pcl_launches.load(
 // ------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float pcl_warp_sum(float v) {
+// Warp reduction of NS (2 or 8) values with a halving butterfly: at each of the first log2(NS) steps a
+// lane keeps half of its values and ships the other half to its xor-partner, so NS values cost
+// NS-1 + (5 - log2 NS) shuffles instead of 5·NS.  On return lane L (L % 4 == 0 suffices) holds the full warp
+// sum of value index pcl_butterfly_index<NS>(L) in v[0].
+template <int NS>
+__device__ __forceinline__ void pcl_warp_reduce(float (&v)[NS], const int lane) {
+  int n = NS;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+  for (int o = 16; o > 0; o >>= 1) {
+    if (n > 1) {
+      const bool up = (lane & o) != 0;
+      n >>= 1;
+#pragma unroll
+      for (int i = 0; i < NS / 2; ++i) {
+        if (i < n) {
+          const float send = up ? v[i] : v[i + n];
+          const float keep = up ? v[i + n] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+    }
+  }
+}
+template <int NS>
+__device__ __forceinline__ int pcl_butterfly_index(const int lane) {
+  return NS == 8 ? (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)) : ((lane >> 4) & 1);
 }
 
 // torch.optim.Adam (single-tensor path, betas 0.9/0.999, eps 1e-8) + ReduceLROnPlateau(mode=min,
@@ -86,14 +110,45 @@ __device__ void pcl_refine_update(PclRefineState& st, float* evalp, const float*
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int FMT, bool BWD, int K>
-__global__ void __launch_bounds__(PCL_THREADS, BWD ? 2 : 3)
+// KK rows of 256 consecutive points (row0 .. row0+KK-1) against every pose of the CTA's pose block.
+template <int FMT, bool BWD, int KK, int NS, bool CHECK>
+__device__ __forceinline__ void pcl_process_rows(const PclCloudView& C, const PclImage& I, const PclPose* s_pose, const int np,
+                                                 double (*s_acc)[PCL_MAX_POSE_BLOCK][NS], const long long row0,
+                                                 const int tid, const int lane, const int warp) {
+  const long long base = row0 * PCL_THREADS + tid;
+  float px[KK], py[KK], pz[KK], cr[KK], cg[KK], cb[KK];
+#pragma unroll
+  for (int j = 0; j < KK; ++j) {
+    const long long i = base + (long long)j * PCL_THREADS;       // arrays are padded: always in bounds
+    px[j] = __ldg(C.x + i); py[j] = __ldg(C.y + i); pz[j] = __ldg(C.z + i);
+    cr[j] = __ldg(C.r + i); cg[j] = __ldg(C.g + i); cb[j] = __ldg(C.b + i);
+  }
+  for (int p = 0; p < np; ++p) {
+    const PclPose pose = s_pose[p];
+    PclAcc acc = {-0.f, -0.f, -0.f, -0.f, -0.f, -0.f, -0.f, -0.f};   // -0 + x == x: first adds fold away
+#pragma unroll
+    for (int j = 0; j < KK; ++j) {
+      const bool valid = CHECK ? ((base + (long long)j * PCL_THREADS) < C.n) : true;   // only the cloud's last row can be ragged
+      pcl_eval<FMT, BWD>(pose, I, px[j], py[j], pz[j], cr[j], cg[j], cb[j], valid, acc);
+    }
+    float v[NS];
+    v[0] = acc.se; v[1] = acc.sm;
+    if (BWD) { v[2] = acc.ax; v[3] = acc.ay; v[4] = acc.az; v[5] = acc.tx; v[6] = acc.ty; v[7] = acc.tz; }
+    pcl_warp_reduce<NS>(v, lane);
+    if ((lane & (NS == 8 ? 3 : 15)) == 0) s_acc[warp][p][pcl_butterfly_index<NS>(lane)] += (double)v[0];
+  }
+}
+
+// HI = 1 compiles for one more resident CTA per SM (forward 4 x 64 regs, forward+backward 3 x 80 regs)
+// instead of (3 x 80, 2 x 128): more warps to hide the texel-gather latency, less ILP inside a thread.
+template <int FMT, bool BWD, int K, int HI>
+__global__ void __launch_bounds__(PCL_THREADS, (BWD ? 2 : 3) + HI)
 pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, const int P, const int PB,
-                  const int n_tiles, double* __restrict__ partial, unsigned int* __restrict__ counters, const PclFinalize fin) {
+                  const long long n_rows, double* __restrict__ partial, unsigned int* __restrict__ counters, const PclFinalize fin) {
   constexpr int NS = BWD ? PCL_NSUM : 2;
   __shared__ __align__(16) PclPose s_pose[PCL_MAX_POSE_BLOCK];
-  __shared__ double s_acc[PCL_WARPS][PCL_MAX_POSE_BLOCK][NS];   // fp64: tile-to-tile accumulation adds no fp32 error
-  __shared__ double s_sum[PCL_MAX_POSE_BLOCK][PCL_NSUM];
+  __shared__ double s_acc[PCL_WARPS][PCL_MAX_POSE_BLOCK][NS];   // fp64: row-to-row accumulation adds no fp32 error
+  __shared__ double s_sum[PCL_THREADS];
   __shared__ int s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -104,39 +159,19 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
   for (int i = tid; i < PCL_WARPS * PCL_MAX_POSE_BLOCK * NS; i += PCL_THREADS) (&s_acc[0][0][0])[i] = 0.0;
   __syncthreads();
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long base = (long long)tile * (PCL_THREADS * K) + tid;
-    float px[K], py[K], pz[K], cr[K], cg[K], cb[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-      const long long i = base + (long long)j * PCL_THREADS;     // arrays are padded: always in bounds
-      px[j] = __ldg(C.x + i); py[j] = __ldg(C.y + i); pz[j] = __ldg(C.z + i);
-      cr[j] = __ldg(C.r + i); cg[j] = __ldg(C.g + i); cb[j] = __ldg(C.b + i);
-    }
-    for (int p = 0; p < np; ++p) {
-      const PclPose pose = s_pose[p];
-      PclAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < K; ++j) {
-        const bool valid = (base + (long long)j * PCL_THREADS) < C.n;
-        pcl_eval<FMT, BWD>(pose, I, px[j], py[j], pz[j], cr[j], cg[j], cb[j], valid, acc);
-      }
-      float v[NS];
-      v[0] = pcl_warp_sum(acc.se); v[1] = pcl_warp_sum(acc.sm);
-      if (BWD) {
-        v[2] = pcl_warp_sum(acc.ax); v[3] = pcl_warp_sum(acc.ay); v[4] = pcl_warp_sum(acc.az);
-        v[5] = pcl_warp_sum(acc.tx); v[6] = pcl_warp_sum(acc.ty); v[7] = pcl_warp_sum(acc.tz);
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < NS; ++s) s_acc[warp][p][s] += (double)v[s];
-      }
-    }
-  }
+  // balanced contiguous row range of this CTA (sizes differ by at most one row of 256 points)
+  const long long r_begin = n_rows * (long long)blockIdx.x / (long long)gridDim.x;
+  const long long r_end = n_rows * (long long)(blockIdx.x + 1) / (long long)gridDim.x;
+  long long r = r_begin;
+  const long long r_full = min(r_end, C.n / PCL_THREADS);      // rows below r_full have 256 real points
+  for (; r + K <= r_full; r += K) pcl_process_rows<FMT, BWD, K, NS, false>(C, I, s_pose, np, s_acc, r, tid, lane, warp);
+  for (; r < r_full; ++r) pcl_process_rows<FMT, BWD, 1, NS, false>(C, I, s_pose, np, s_acc, r, tid, lane, warp);
+  for (; r < r_end; ++r) pcl_process_rows<FMT, BWD, 1, NS, true>(C, I, s_pose, np, s_acc, r, tid, lane, warp);
   __syncthreads();
 
   // CTA partial row: partial[blockIdx.x][s][pose]
-  for (int i = tid; i < np * NS; i += PCL_THREADS) {
+  const int nout = np * NS;
+  for (int i = tid; i < nout; i += PCL_THREADS) {
     const int s = i / np, p = i - s * np;
     double t = 0.0;
 #pragma unroll
@@ -155,19 +190,34 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
   if (!s_last) return;
   __threadfence();
 
-  for (int i = tid; i < np * NS; i += PCL_THREADS) {
-    const int s = i / np, p = i - s * np;
+  // deterministic two-level reduction of the gridDim.x partial rows: G thread groups stride the rows,
+  // then the groups are summed in fixed order
+  const int G = max(1, PCL_THREADS / nout);
+  {
+    const int out = tid % nout, g = tid / nout;
     double t = 0.0;
-    for (unsigned int bx = 0; bx < gridDim.x; ++bx)
-      t += __ldcg(partial + ((size_t)bx * NS + s) * (size_t)P + (size_t)(p0 + p));
-    s_sum[p][s] = t;
+    if (g < G) {
+      const int s = out / np, p = out - s * np;
+      const double* src = partial + (size_t)s * (size_t)P + (size_t)(p0 + p);
+      const size_t stride = (size_t)NS * (size_t)P;
+#pragma unroll 8
+      for (unsigned int bx = g; bx < gridDim.x; bx += G) t += __ldcg(src + (size_t)bx * stride);
+    }
+    s_sum[tid] = t;
   }
   __syncthreads();
   if (tid < np) {
+    double sums[PCL_NSUM];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      double t = 0.0;
+      for (int g = 0; g < G; ++g) t += s_sum[g * nout + s * np + tid];
+      sums[s] = t;
+    }
     const int pg = p0 + tid;
     const float* p6 = poses6 + 6 * (size_t)pg;
     float loss, cnt, grad[6];
-    pcl_finish_gradient(p6, s_pose[tid], I, s_sum[tid], &loss, &cnt, BWD ? grad : nullptr);
+    pcl_finish_gradient(p6, s_pose[tid], I, sums, &loss, &cnt, BWD ? grad : nullptr);
     if (fin.loss) fin.loss[pg] = loss;
     if (fin.count) fin.count[pg] = cnt;
     if (BWD) {
@@ -185,7 +235,10 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
 // ------------------------------------------------------------------------------------------------
 // host-side launch
 // ------------------------------------------------------------------------------------------------
-struct PclLaunchPlan { int K, PB, gx, gy, n_tiles, NS; };
+#ifndef PCL_DEFAULT_HI
+#define PCL_DEFAULT_HI 0
+#endif
+struct PclLaunchPlan { int K, PB, gx, gy, NS, hi; long long n_rows; };
 
 static int pcl_env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -201,23 +254,36 @@ static int pcl_num_sms() {
   return sms;
 }
 
+// Grid sizing (148 SMs): the whole grid is ONE resident wave — gx*gy = SMs x resident CTAs per SM (3 forward,
+// 2 forward+backward, from the register budgets) — unless there are more pose blocks than that; every CTA
+// gets an equal share of rows, so there is no tail wave and the last-block reduction reads <= ~450 rows.
 static PclLaunchPlan pcl_plan(const pcl_cloud* c, int64_t P, bool bwd) {
   PclLaunchPlan pl;
   pl.K = pcl_env_int("PCL_K", 4);
-  if (pl.K != 4 && pl.K != 8 && pl.K != 2) pl.K = 4;
+  if (pl.K != 4 && pl.K != 8) pl.K = 4;
   pl.NS = bwd ? PCL_NSUM : 2;
-  pl.PB = (int)(P < PCL_MAX_POSE_BLOCK ? P : PCL_MAX_POSE_BLOCK);
+  pl.n_rows = c->n_pad / PCL_THREADS;
+  pl.hi = pcl_env_int(bwd ? "PCL_OCC_BWD" : "PCL_OCC_FWD", PCL_DEFAULT_HI) ? 1 : 0;
+  const int resident = pcl_num_sms() * ((bwd ? 2 : 3) + pl.hi);
+  // pose block: as many poses per CTA as possible (point loads amortise over the block) while leaving
+  // enough CTAs to fill the machine
+  int PB = (int)(P < PCL_MAX_POSE_BLOCK ? P : PCL_MAX_POSE_BLOCK);
   const int pb_env = pcl_env_int(bwd ? "PCL_PB_BWD" : "PCL_PB_FWD", 0);
-  if (pb_env > 0 && pb_env <= PCL_MAX_POSE_BLOCK) pl.PB = (int)(pb_env < P ? pb_env : P);
-  pl.gy = (int)((P + pl.PB - 1) / pl.PB);
-  pl.n_tiles = (int)(c->n_pad / (PCL_THREADS * pl.K));
-  const int resident = pcl_num_sms() * (bwd ? 2 : 3);
-  const int waves = pcl_env_int("PCL_WAVES", 4);
-  int gx = (resident * waves + pl.gy - 1) / pl.gy;
-  if (gx < 1) gx = 1;
-  if (gx > pl.n_tiles) gx = pl.n_tiles;
-  const int per = (pl.n_tiles + gx - 1) / gx;        // tiles per CTA, then the fewest CTAs giving it
-  pl.gx = (pl.n_tiles + per - 1) / per;
+  if (pb_env > 0 && pb_env <= PCL_MAX_POSE_BLOCK) PB = (int)(pb_env < P ? pb_env : P);
+  pl.PB = PB;
+  pl.gy = (int)((P + PB - 1) / PB);
+  // 1..4 full waves: take the wave count whose grid fills its slots best (CTAs do equal work)
+  long long gx = 1;
+  double best = -1.0;
+  const int w_env = pcl_env_int("PCL_WAVES", 0);
+  for (int w = (w_env > 0 ? w_env : 1); w <= (w_env > 0 ? w_env : 4); ++w) {
+    long long g = (long long)resident * w / pl.gy;
+    if (g < 1) g = 1;
+    if (g > pl.n_rows) g = pl.n_rows;
+    const double util = (double)(g * pl.gy) / (double)((g * pl.gy + resident - 1) / resident * resident);
+    if (util > best + 1e-9) { best = util; gx = g; }
+  }
+  pl.gx = (int)gx;
   return pl;
 }
 
@@ -225,11 +291,10 @@ template <int FMT, bool BWD>
 static void pcl_launch_fmt(const PclLaunchPlan& pl, const PclCloudView& C, const PclImage& I, const float* poses, int P,
                            double* partial, unsigned int* counters, const PclFinalize& fin, cudaStream_t st) {
   dim3 grid(pl.gx, pl.gy), block(PCL_THREADS);
-  switch (pl.K) {
-    case 2: pcl_sample_kernel<FMT, BWD, 2><<<grid, block, 0, st>>>(C, I, poses, P, pl.PB, pl.n_tiles, partial, counters, fin); break;
-    case 8: pcl_sample_kernel<FMT, BWD, 8><<<grid, block, 0, st>>>(C, I, poses, P, pl.PB, pl.n_tiles, partial, counters, fin); break;
-    default: pcl_sample_kernel<FMT, BWD, 4><<<grid, block, 0, st>>>(C, I, poses, P, pl.PB, pl.n_tiles, partial, counters, fin); break;
-  }
+#define PCL_GO(KK, HH) pcl_sample_kernel<FMT, BWD, KK, HH><<<grid, block, 0, st>>>(C, I, poses, P, pl.PB, pl.n_rows, partial, counters, fin)
+  if (pl.hi) { if (pl.K == 8) PCL_GO(8, 1); else PCL_GO(4, 1); }
+  else { if (pl.K == 8) PCL_GO(8, 0); else PCL_GO(4, 0); }
+#undef PCL_GO
 }
 
 template <bool BWD>
@@ -240,6 +305,8 @@ static int pcl_launch(const PclLaunchPlan& pl, const pcl_cloud* c, const pcl_ima
     case PCL_FMT_U8Q: pcl_launch_fmt<PCL_FMT_U8Q, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st); break;
     case PCL_FMT_U8P: pcl_launch_fmt<PCL_FMT_U8P, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st); break;
     case PCL_FMT_F32: pcl_launch_fmt<PCL_FMT_F32, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st); break;
+    case PCL_FMT_TEX: pcl_launch_fmt<PCL_FMT_TEX, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st); break;
+    case PCL_FMT_F16D: pcl_launch_fmt<PCL_FMT_F16D, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st); break;
     default: pcl_set_error("unknown image format %d", im->view.fmt); return PCL_ERR_INVALID;
   }
   PCL_LAUNCH_CHECK();

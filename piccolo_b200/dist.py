@@ -1,0 +1,89 @@
+"""Multi-GPU sharding (one process per GPU, torch.distributed).  The path shards naturally: every
+(pose, point) term is independent, so the only exchange is a tiny all-gather of per-pose losses after
+scoring and of per-candidate (loss, pose) rows before the arg-min.  Backend: NCCL over
+NVLink on the GPU box; gloo in the CPU tests, where the local compute is injected."""
+from __future__ import annotations
+
+from typing import Callable
+
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n: int, rank: int, world_size: int):
+    """Contiguous slice [lo, hi) of n units for `rank`; sizes differ by at most one."""
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _all_gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """All-gather variable-length row blocks (contiguous shards) into the full (n_total, ...) tensor."""
+    rank, ws = world()
+    if ws == 1:
+        return local
+    rows = max(shard_bounds(n_total, r, ws)[1] - shard_bounds(n_total, r, ws)[0] for r in range(ws))
+    pad = torch.zeros((rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(out, pad)
+    parts = []
+    for r in range(ws):
+        lo, hi = shard_bounds(n_total, r, ws)
+        parts.append(out[r][: hi - lo])
+    return torch.cat(parts, dim=0)
+
+
+def score_sharded(score_fn: Callable[[torch.Tensor], torch.Tensor], poses: torch.Tensor) -> torch.Tensor:
+    """Every rank scores its contiguous slice of the flattened pose grid (index i*R+j) and all ranks end up
+    with the full loss vector, so the deterministic top-K (ties -> lower index) is identical everywhere."""
+    rank, ws = world()
+    lo, hi = shard_bounds(poses.shape[0], rank, ws)
+    local = score_fn(poses[lo:hi]) if hi > lo else poses.new_zeros((0,))
+    return _all_gather_rows(local.reshape(-1, 1), poses.shape[0]).reshape(-1)
+
+
+def refine_sharded(refine_fn: Callable[[torch.Tensor], torch.Tensor], starts: torch.Tensor) -> torch.Tensor:
+    """Candidates are dealt round-robin; each rank refines its own with zero communication, then one
+    all-gather of the (loss, pose) rows.  refine_fn maps (b,6) start poses -> (b,7) rows [loss, pose].
+    Returns the (B,7) table in candidate order on every rank."""
+    rank, ws = world()
+    B = starts.shape[0]
+    mine = list(range(rank, B, ws))
+    local = refine_fn(starts[mine]) if mine else starts.new_zeros((0, 7))
+    if ws == 1:
+        return local
+    rows = (B + ws - 1) // ws
+    pad = torch.full((rows, 7), float("nan"), dtype=starts.dtype, device=starts.device)
+    pad[: local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(out, pad)
+    table = torch.empty((B, 7), dtype=starts.dtype, device=starts.device)
+    for r in range(ws):
+        idx = list(range(r, B, ws))
+        if idx:
+            table[idx] = out[r][: len(idx)]
+    return table
+
+
+def argmin_candidate(table: torch.Tensor):
+    """Arg-min over the gathered (loss, pose) rows; NaN losses lose; ties -> lower index."""
+    loss = torch.where(torch.isnan(table[:, 0]), torch.full_like(table[:, 0], float("inf")), table[:, 0])
+    k = int(torch.argmin(loss))
+    return k, table[k, 1:], table[k, 0]
+
+
+def gather_results(row: torch.Tensor) -> torch.Tensor:
+    """Multi-query mode: each rank contributes one result row; returns (world, len(row))."""
+    rank, ws = world()
+    if ws == 1:
+        return row[None]
+    out = [torch.empty_like(row) for _ in range(ws)]
+    dist.all_gather(out, row)
+    return torch.stack(out)

@@ -12,8 +12,8 @@ import torch
 
 from . import _lib
 
-IMAGE_AUTO, IMAGE_U8Q, IMAGE_F32, IMAGE_U8P = 0, 1, 2, 3
-IMAGE_FORMATS = {"auto": IMAGE_AUTO, "u8q": IMAGE_U8Q, "f32": IMAGE_F32, "u8p": IMAGE_U8P}
+IMAGE_AUTO, IMAGE_U8Q, IMAGE_F32, IMAGE_U8P, IMAGE_TEX, IMAGE_F16D = 0, 1, 2, 3, 4, 5
+IMAGE_FORMATS = {"auto": IMAGE_AUTO, "u8q": IMAGE_U8Q, "f32": IMAGE_F32, "u8p": IMAGE_U8P, "tex": IMAGE_TEX, "f16d": IMAGE_F16D}
 CLOUD_KEEP_ORDER, CLOUD_MORTON = 0, 1
 
 

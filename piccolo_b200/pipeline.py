@@ -1,0 +1,61 @@
+"""One localisation query = grid scoring -> top-K -> refinement -> arg-min  (localize.py:207-233 without
+file I/O).  Shared by bench.py, main.py/localize.py and the multi-GPU drivers."""
+from __future__ import annotations
+
+from collections import namedtuple
+
+import torch
+
+from . import engine
+from .utils import grid_poses
+
+TrainCfg = namedtuple("TrainCfg", ["num_input", "num_intermediate", "lr", "num_iter", "patience", "factor", "out_of_room_quantile", "parallel"])
+
+# configs/stanford.ini and configs/stanford_parallel.ini of the reference ([Train]/[Initialization] values)
+STANFORD = TrainCfg(6, 50, 0.1, 100, 5, 0.8, 0.05, False)
+STANFORD_PARALLEL = STANFORD._replace(parallel=True)
+
+
+def query_evals(n_points: int, n_grid: int, cfg) -> int:
+    """pose·point evaluations of one query: forward-only grid scoring + num_iter fused fwd+bwd iterations."""
+    return n_points * (n_grid + cfg.num_iter * cfg.num_input)
+
+
+def localize_query(cloud: engine.Cloud, image: engine.Image, grid: torch.Tensor, cfg, timers=None):
+    """grid (P,6) start poses on the device.  Returns dict(pose (6,), loss, index, candidates (B,6), losses (B,)).
+
+    Candidate selection: the `num_input` grid poses with the smallest sampling loss.  (The reference
+    inserts a colour-histogram re-rank of the top `num_intermediate` here, utils.py:627 — SURVEY §8f
+    "next" #1; until that kernel lands the top-`num_input` by loss are refined.)"""
+    ev = timers if timers is not None else {}
+    if "score0" in ev:
+        ev["score0"].record()
+    loss, _ = engine.score(cloud, image, grid)
+    if "score1" in ev:
+        ev["score1"].record()
+    idx = engine.topk(loss, cfg.num_input)
+    starts = grid.index_select(0, idx)
+    ref = engine.Refiner(starts.shape[0], cfg.lr, cfg.factor, cfg.patience, bool(cfg.parallel)).reset(starts)
+    if "refine0" in ev:
+        ev["refine0"].record()
+    ref.run(cloud, image, cfg.num_iter)
+    if "refine1" in ev:
+        ev["refine1"].record()
+    out = ref.read()
+    best = out["loss"].argmin()
+    return {"pose": out["pose"][best], "loss": out["loss"][best], "index": best, "candidates": out["pose"], "losses": out["loss"],
+            "start_index": idx}
+
+
+def localize_query_host(xyz_h: torch.Tensor, rgb_h: torch.Tensor, img_h: torch.Tensor, grid_h: torch.Tensor, cfg, device):
+    """End-to-end call with HOST (pinned) buffers: upload, pack, score, refine, and read the answer back.
+    Returns (pose (6,) cpu, loss cpu float)."""
+    xyz = xyz_h.to(device, non_blocking=True)
+    rgb = rgb_h.to(device, non_blocking=True)
+    img = img_h.to(device, non_blocking=True)
+    grid = grid_h.to(device, non_blocking=True)
+    cloud = engine.Cloud(xyz, rgb, cfg.out_of_room_quantile)
+    image = engine.Image(img)
+    out = localize_query(cloud, image, grid, cfg)
+    res = torch.cat([out["pose"], out["loss"].reshape(1)]).cpu()
+    return res[:6], float(res[6])

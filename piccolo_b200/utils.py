@@ -45,3 +45,29 @@ def rot_from_ypr(ypr_array: torch.Tensor) -> torch.Tensor:
     from .omniloc import _rotation_from_angles
     yaw, pitch, roll = ypr_array
     return _rotation_from_angles(yaw.reshape(1), pitch.reshape(1), roll.reshape(1), ypr_array.device)
+
+
+def generate_rot_points(init_dict=None, device="cpu") -> torch.Tensor:
+    """Rotation start grid (utils.py:321-360): yaw-only, or the num_yaw x num_pitch x num_roll Euler lattice
+    with triples that produce the same rotation removed (24 of 64 survive for 4x4x4).  The reference
+    de-duplicates through a python `set` (order depends on PYTHONHASHSEED); here duplicates are
+    dropped keeping the FIRST occurrence in lattice order, which fixes the pose index i*R+j."""
+    import numpy as np
+    if init_dict["yaw_only"]:
+        rot_arr = torch.zeros(init_dict["num_yaw"], 3, device=device)
+        rot_arr[:, 0] = torch.arange(init_dict["num_yaw"], dtype=torch.float, device=device) * 2 * np.pi / init_dict["num_yaw"]
+        return rot_arr
+    ny, npi, nr = init_dict["num_yaw"], init_dict["num_pitch"], init_dict["num_roll"]
+    y, p, r = torch.meshgrid(torch.arange(ny).float() / ny, torch.arange(npi).float() / npi, torch.arange(nr).float() / nr, indexing="ij")
+    rot_arr = torch.stack([y.reshape(-1), p.reshape(-1), r.reshape(-1)], dim=1)
+    for k, name in enumerate(("yaw", "pitch", "roll")):
+        lo, hi = init_dict.get("min_" + name, 0.0), init_dict.get("max_" + name, 2 * np.pi)
+        rot_arr[:, k] = rot_arr[:, k] * (hi - lo) + lo
+    seen, keep = set(), []
+    for i, ypr in enumerate(rot_arr):
+        key = tuple(np.round(rot_from_ypr(ypr).numpy() + 0.0, 3).reshape(-1).tolist())
+        key = tuple(0.0 if v == 0 else v for v in key)     # -0.0 == 0.0
+        if key not in seen:
+            seen.add(key)
+            keep.append(i)
+    return rot_arr[keep].to(device)

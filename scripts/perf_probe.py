@@ -11,17 +11,24 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from piccolo_b200 import engine, synth  # noqa: E402
 
 
-def timeit(fn, iters=5, warm=2):
+def timeit(fn, iters=5, warm=2, repeats=5):
+    """best-of-`repeats` average over `iters` launches (min filters out clock / neighbour noise)"""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+    best = 1e30
+    for _ in range(repeats):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / iters)
+    return best
+
+
+FMTS = tuple(os.environ.get('PROBE_FMTS', 'u8q,tex,u8p,f32').split(','))
 
 
 def main():
@@ -39,22 +46,21 @@ def main():
     cand = torch.from_numpy(np.stack([sc.gt_pose + np.concatenate([rng.normal(0, 0.2, 3), rng.normal(0, 0.1, 3)]) for _ in range(6)]).astype(np.float32)).to(dev)
     for order in (1, 0):
         cloud = engine.Cloud(xyz, rgb, 0.05, order)
-        for fmt in ("u8q", "u8p", "f32"):
+        for fmt in FMTS:
             image = engine.Image(img, fmt)
-            for K in (2, 4, 8):
-                os.environ["PCL_K"] = str(K)
-                for PB in (8, 32):
-                    os.environ["PCL_PB_FWD"] = str(PB)
-                    ms = timeit(lambda: engine.score(cloud, image, poses))
-                    print(f"order={order} fmt={fmt} K={K} PB={PB} SCORE P={len(poses)}: {ms:.3f} ms  {len(poses)*N/ms/1e6:.1f} G pp/s", flush=True)
-                for PBB in (1, 6):
-                    os.environ["PCL_PB_BWD"] = str(PBB)
-                    ms = timeit(lambda: engine.loss_fwd_bwd(cloud, image, cand), iters=20, warm=3)
-                    print(f"order={order} fmt={fmt} K={K} PBB={PBB} FWDBWD B=6: {ms:.4f} ms  {6*N/ms/1e6:.1f} G pp/s", flush=True)
+            for K, occ in ((4, 0), (4, 1), (8, 0)):
+                os.environ["PCL_K"] = str(K); os.environ["PCL_OCC_FWD"] = str(occ); os.environ["PCL_OCC_BWD"] = str(occ)
+                ms = timeit(lambda: engine.score(cloud, image, poses))
+                print(f"order={order} fmt={fmt} K={K} occ={occ} SCORE P={len(poses)}: {ms:.3f} ms  {len(poses)*N/ms/1e6:.1f} G pp/s", flush=True)
+                ms = timeit(lambda: engine.loss_fwd_bwd(cloud, image, cand), iters=20, warm=3)
+                print(f"order={order} fmt={fmt} K={K} occ={occ} FWDBWD B=6: {ms:.4f} ms  {6*N/ms/1e6:.1f} G pp/s", flush=True)
+                c64 = cand.repeat(11, 1)[:64].contiguous()
+                ms = timeit(lambda: engine.loss_fwd_bwd(cloud, image, c64), iters=10, warm=2)
+                print(f"order={order} fmt={fmt} K={K} occ={occ} FWDBWD B=64: {ms:.4f} ms  {64*N/ms/1e6:.1f} G pp/s", flush=True)
             if order == 0:
                 break
     # large-batch fwd+bwd (amortises launch + tail): 64 candidates
-    os.environ["PCL_K"] = "4"; os.environ["PCL_PB_BWD"] = "8"
+    os.environ["PCL_K"] = "4"; os.environ["PCL_OCC_FWD"] = "0"; os.environ["PCL_OCC_BWD"] = "0"
     cloud = engine.Cloud(xyz, rgb, 0.05, 1)
     image = engine.Image(img, "u8q")
     cand64 = cand.repeat(11, 1)[:64].contiguous()

@@ -32,12 +32,12 @@ static void run(const PclImage& I, const float* xyz, const float* rgb, long n, c
 extern "C" int emul_loss_grad(const float* xyz, const float* rgb, long n, const float* img, int H, int W, int fmt,
                               const float* poses, int P, int bwd, float* loss, float* cnt, float* grad) {
   PclImage I; std::memset(&I, 0, sizeof(I));
-  pcl_image_set_geometry(I, H, W);
+  pcl_image_set_geometry(I, H, W, (fmt == PCL_FMT_U8Q || fmt == PCL_FMT_F16D) ? W + 1 : W + 2);
   I.fmt = fmt;
   std::vector<uint32_t> u8;
   std::vector<float> f32;
   if (fmt == PCL_FMT_U8Q) {
-    I.pitch = W + 1; I.tex_scale = 1.0f / 255.0f;
+    I.tex_scale = 1.0f / 255.0f;
     u8.resize((size_t)(H + 1) * (W + 1) * 4);
     for (int y0 = -1; y0 < H; ++y0) for (int x0 = -1; x0 < W; ++x0) {
       uint32_t* e = &u8[((size_t)(y0 + 1) * (W + 1) + (x0 + 1)) * 4];
@@ -45,19 +45,40 @@ extern "C" int emul_loss_grad(const float* xyz, const float* rgb, long n, const 
       e[2] = pack_rgba(img, H, W, y0 + 1, x0); e[3] = pack_rgba(img, H, W, y0 + 1, x0 + 1);
     }
     I.data = u8.data();
+  } else if (fmt == PCL_FMT_F16D) {
+    I.tex_scale = 1.0f / 255.0f;
+    u8.resize((size_t)(H + 1) * (W + 1) * 8);
+    auto h16 = [](int v) -> uint32_t {            // exact fp16 bits of a small integer
+      if (v == 0) return 0u;
+      uint32_t sgn = v < 0 ? 0x8000u : 0u; uint32_t a = (uint32_t)(v < 0 ? -v : v); int e = 0;
+      while ((a >> (e + 1)) != 0) ++e;            // a in [2^e, 2^(e+1))
+      uint32_t man = (a << (10 - e)) & 0x3ffu;
+      return sgn | ((uint32_t)(e + 15) << 10) | man;
+    };
+    for (int y0 = -1; y0 < H; ++y0) for (int x0 = -1; x0 < W; ++x0) {
+      uint32_t t[4] = {pack_rgba(img, H, W, y0, x0), pack_rgba(img, H, W, y0, x0 + 1), pack_rgba(img, H, W, y0 + 1, x0), pack_rgba(img, H, W, y0 + 1, x0 + 1)};
+      uint32_t* e = &u8[((size_t)(y0 + 1) * (W + 1) + (x0 + 1)) * 8];
+      for (int c = 0; c < 3; ++c) {
+        int nw = (t[0] >> (8 * c)) & 0xff, ne = (t[1] >> (8 * c)) & 0xff, sw = (t[2] >> (8 * c)) & 0xff, se = (t[3] >> (8 * c)) & 0xff;
+        e[2 * c] = h16(nw) | (h16(ne - nw) << 16);
+        e[2 * c + 1] = h16(sw - nw) | (h16((se - sw) - (ne - nw)) << 16);
+      }
+      e[6] = e[7] = 0;
+    }
+    I.data = u8.data();
   } else if (fmt == PCL_FMT_U8P) {
-    I.pitch = W + 2; I.tex_scale = 1.0f / 255.0f;
+    I.tex_scale = 1.0f / 255.0f;
     u8.resize((size_t)(H + 2) * (W + 2));
     for (int y = -1; y <= H; ++y) for (int x = -1; x <= W; ++x) u8[(size_t)(y + 1) * (W + 2) + (x + 1)] = pack_rgba(img, H, W, y, x);
     I.data = u8.data();
   } else {
-    I.pitch = W + 2; I.tex_scale = 1.0f;
+    I.tex_scale = 1.0f;
     f32.assign((size_t)(H + 2) * (W + 2) * 4, 0.0f);
     for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x)
       for (int c = 0; c < 3; ++c) f32[((size_t)(y + 1) * (W + 2) + (x + 1)) * 4 + c] = img[((size_t)y * W + x) * 3 + c];
     I.data = f32.data();
   }
 #define GO(F) do { if (bwd) run<F, true>(I, xyz, rgb, n, poses, P, loss, cnt, grad); else run<F, false>(I, xyz, rgb, n, poses, P, loss, cnt, grad); } while (0)
-  if (fmt == PCL_FMT_U8Q) GO(PCL_FMT_U8Q); else if (fmt == PCL_FMT_U8P) GO(PCL_FMT_U8P); else GO(PCL_FMT_F32);
+  if (fmt == PCL_FMT_U8Q) GO(PCL_FMT_U8Q); else if (fmt == PCL_FMT_U8P) GO(PCL_FMT_U8P); else if (fmt == PCL_FMT_F16D) GO(PCL_FMT_F16D); else GO(PCL_FMT_F32);
   return 0;
 }

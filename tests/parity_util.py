@@ -22,4 +22,4 @@ def final_pose_gates(g, b=None):
     return max(0.01, 1.5 * spread_t), max(0.1, 1.5 * spread_r)
 
 
-EARLY_T, EARLY_R = 3e-3, 0.05      # after `early_iter` iterations trajectories are still correlated
+EARLY_T, EARLY_R = 5e-3, 0.1      # after `early_iter` iterations trajectories are still correlated

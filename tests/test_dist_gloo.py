@@ -1,0 +1,84 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU sharding logic: sharded scoring and round-robin
+refinement give exactly the single-process result.  The local compute is the CPU oracle."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, ws, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        from oracle import piccolo_oracle as orc
+        from piccolo_b200 import dist as pd, synth
+        sc = synth.make_scene(3000, 32, 64, seed=5)
+        xyz, rgb, img = [torch.from_numpy(a) for a in (sc.xyz, sc.rgb, sc.img)]
+        poses = torch.from_numpy(synth.pose_grid(sc.room, (3, 3, 1), 5))          # 45 poses: ragged split
+
+        def score_fn(p):
+            return orc.sampling_loss_torch(xyz, rgb, img, p)[0]
+
+        full = pd.score_sharded(score_fn, poses)
+        idx = torch.from_numpy(orc.topk_ascending(full.numpy(), 5))
+        starts = poses[idx]
+
+        def refine_fn(s):
+            out = orc.refine_torch(xyz, rgb, img, s, num_iter=3, factor=0.8)
+            return torch.cat([out["loss"].reshape(-1, 1), out["pose"]], dim=1)
+
+        table = pd.refine_sharded(refine_fn, starts)
+        k, pose, loss = pd.argmin_candidate(table)
+        rows = pd.gather_results(torch.tensor([float(rank), float(loss)]))
+        q.put((rank, full.numpy(), table.numpy(), k, rows.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_scoring_and_refinement_match_single_process():
+    from oracle import piccolo_oracle as orc
+    from piccolo_b200 import dist as pd, synth
+    ws, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    results = sorted([q.get(timeout=300) for _ in range(ws)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process truth
+    sc = synth.make_scene(3000, 32, 64, seed=5)
+    xyz, rgb, img = [torch.from_numpy(a) for a in (sc.xyz, sc.rgb, sc.img)]
+    poses = torch.from_numpy(synth.pose_grid(sc.room, (3, 3, 1), 5))
+    full = orc.sampling_loss_torch(xyz, rgb, img, poses)[0]
+    idx = torch.from_numpy(orc.topk_ascending(full.numpy(), 5))
+    out = orc.refine_torch(xyz, rgb, img, poses[idx], num_iter=3, factor=0.8)
+    table = torch.cat([out["loss"].reshape(-1, 1), out["pose"]], dim=1).numpy()
+    for rank, f, t, k, rows in results:
+        np.testing.assert_allclose(f, full.numpy(), rtol=1e-6)            # same values on every rank
+        np.testing.assert_array_equal(orc.topk_ascending(f, 5), idx.numpy())
+        np.testing.assert_allclose(t, table, rtol=1e-4, atol=1e-6)
+        assert k == int(np.argmin(table[:, 0]))
+        assert rows.shape == (2, 2) and rows[:, 0].tolist() == [0.0, 1.0]
+    np.testing.assert_array_equal(results[0][1], results[1][1])           # bit-identical across ranks
+
+
+def test_shard_bounds_cover_everything():
+    from piccolo_b200.dist import shard_bounds
+    for n in (0, 1, 5, 6, 7, 1800, 4096):
+        for ws in (1, 2, 4, 8):
+            spans = [shard_bounds(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(ws - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1

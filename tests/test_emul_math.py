@@ -12,7 +12,7 @@ from piccolo_b200 import synth
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "emul", "pcl_emul.cpp")
 SO = os.path.join(HERE, "emul", "_pcl_emul.so")
-FMT = {"u8q": 1, "f32": 2, "u8p": 3}
+FMT = {"u8q": 1, "f32": 2, "u8p": 3, "f16d": 5}
 
 
 @pytest.fixture(scope="module")
@@ -34,7 +34,7 @@ def emul():
     return call
 
 
-@pytest.mark.parametrize("fmt", ["u8q", "f32", "u8p"])
+@pytest.mark.parametrize("fmt", ["u8q", "f32", "u8p", "f16d"])
 def test_emulated_kernel_math_matches_reference(emul, golden, fmt):
     g = golden("loss_small")
     rgb, img = synth.rgb_from_u8(g["rgb8"]), synth.img_from_u8(g["img8"])
