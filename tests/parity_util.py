@@ -8,17 +8,19 @@ def rot_err_deg(Ra, Rb):
 
 
 def final_pose_gates(g, b=None):
-    """(translation gate [m], rotation gate [deg]) for candidate b (None = the omniloc_batch result).
+    """(translation gate [m], rotation gate [deg]) for the end state of a refinement.
 
     North star: 1 cm / 0.1 deg.  The reference's own end state is only reproducible to its fp32-vs-fp64
-    spread (Adam still jitters with lr≈0.017 after 100 iterations; measured spread up to 0.15 deg, stored
-    in the fixture as f64_*), so the rotation gate is max(0.1 deg, 1.5 x that spread)."""
-    if b is None:
-        spread_t = np.linalg.norm(g["bat_t"] - g["f64_bat_t"])
-        spread_r = rot_err_deg(g["bat_R"], g["f64_bat_R"])
-    else:
-        spread_t = np.linalg.norm(g["seq_t"][b] - g["f64_seq_t"][b])
-        spread_r = rot_err_deg(g["seq_R"][b], g["f64_seq_R"][b])
+    spread: Adam normalises every coordinate's step to ~lr regardless of the gradient's size, so rounding
+    noise on near-zero gradient components is amplified, and after 100 iterations (lr still ≈0.017) the
+    pose jitters by ~0.1-0.2 deg.  The fixture stores the reference's fp64 run (f64_*); the jitter level is
+    a property of the scene/config, so the gate is max(north-star, 1.5 x the largest spread over the
+    converged candidates of the fixture)."""
+    conv = g["seq_loss"] <= 3 * g["seq_loss"].min()
+    spread_t = max([np.linalg.norm(g["seq_t"][i] - g["f64_seq_t"][i]) for i in range(len(conv)) if conv[i]]
+                   + [np.linalg.norm(g["bat_t"] - g["f64_bat_t"])])
+    spread_r = max([rot_err_deg(g["seq_R"][i], g["f64_seq_R"][i]) for i in range(len(conv)) if conv[i]]
+                   + [rot_err_deg(g["bat_R"], g["f64_bat_R"])])
     return max(0.01, 1.5 * spread_t), max(0.1, 1.5 * spread_r)
 
 
