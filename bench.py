@@ -36,6 +36,7 @@ import torch  # noqa: E402
 ALGO_BYTES_PER_EVAL = 24.0   # one point = xyz 3xf32 + rgb 3xf32
 METRIC = "pose_point_loss_evals_per_sec"
 UNIT = "pose*point/s"
+SCENE_SEED = 3   # seeded synthetic room whose query the reference algorithm itself localises (top-6 by loss reach the GT basin)
 
 
 def measured_hbm_peak():
@@ -128,7 +129,7 @@ def run_reference(args):
         return
     from piccolo_b200 import pipeline, synth
     cfg = pipeline.STANFORD_PARALLEL
-    sc = synth.make_scene(args.n_points, args.height, 2 * args.height, seed=2)
+    sc = synth.make_scene(args.n_points, args.height, 2 * args.height, seed=SCENE_SEED)
     grid = stanford_grid(sc, "cpu")
     n_score, n_iter = 12, 1
     for _ in range(args.warmup):
@@ -174,9 +175,9 @@ def run_ours(args):
     cfg = pipeline.STANFORD_PARALLEL
 
     # one cloud per room (replicated), one query panorama per rank
-    sc = synth.make_scene(args.n_points, args.height, 2 * args.height, seed=2)
+    sc = synth.make_scene(args.n_points, args.height, 2 * args.height, seed=SCENE_SEED)
     if rank > 0:
-        gt = synth.random_gt_pose(sc.room, seed=2 + rank)
+        gt = synth.random_gt_pose(sc.room, seed=SCENE_SEED + rank)
         sc = synth.Scene(sc.xyz, sc.rgb8, synth.render_panorama(gt, args.height, 2 * args.height, sc.room), gt, sc.room)
     grid = stanford_grid(sc, device)
     P = grid.shape[0]
