@@ -92,6 +92,13 @@ int pcl_score(const pcl_cloud* c, const pcl_image* im, const float* poses_p6_dev
 /* indices of the k smallest losses, ascending, ties -> lower index, NaN last */
 int pcl_topk(const float* loss_p_dev, int64_t p, int k, int64_t* idx_k_dev, void* stream);
 
+/* ---- colour-histogram re-rank of K scored candidates (trim_input_hist_secondary, utils.py:510-588) ------- */
+/* Renders the cloud from each pose (painter's order of make_pano, utils.py:134-205) and intersects 8x8x8 colour
+ * histograms of the middle num_split_h-2 row blocks with the query's.  img_hw3_dev: the (H,W,3) float32 query
+ * panorama.  hist_intersect_k_dev[k] = the reference's `hist_intersect` (larger is better). */
+int pcl_hist_rerank(const pcl_cloud* c, const float* img_hw3_dev, int h, int w, const float* poses_k6_dev, int k,
+                    int num_split_h, int num_split_w, float* hist_intersect_k_dev, void* stream);
+
 /* ---- loss + analytic 6-DoF gradient of B poses (autograd.Function backend) ------------------- */
 /* grad_b6_dev[b] = d loss_b / d (tx,ty,tz,yaw,pitch,roll) */
 int pcl_loss_fwd_bwd(const pcl_cloud* c, const pcl_image* im, const float* poses_b6_dev, int b,

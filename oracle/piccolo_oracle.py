@@ -364,3 +364,73 @@ def refine_torch(xyz, rgb, img, poses0, lr=0.1, num_iter=100, patience=5, factor
                 leaves[b][:3] = torch.minimum(torch.maximum(leaves[b][:3], lo), hi)
     param = torch.stack([l.detach().clone() for l in leaves])
     return {"pose": evalp if batch_semantics else param, "loss": last, "param": param}
+
+
+# --------------------------------------------------------------------------------------
+# histogram re-rank: make_pano + histogram + trim_input_hist_secondary
+# --------------------------------------------------------------------------------------
+def make_pano_np(xyz_cam, rgb, H, W):
+    """make_pano (utils.py:134-205), CPU semantics: painter's algorithm by nine index_put_ calls in a fixed
+    order (neighbours first, centre last), far points first inside a call, last write wins.
+    xyz_cam (N,3) float32 camera-frame points.  Returns float32 (H,W,3) = rgb*255 (0 where nothing landed)."""
+    xyz_cam = np.asarray(xyz_cam, dtype=np.float32)
+    rgb = np.asarray(rgb, dtype=np.float32)
+    dist = np.sqrt(np.sum(xyz_cam * xyz_cam, axis=1, dtype=np.float32))
+    order = np.argsort(dist, kind="stable")[::-1]
+    q, col = xyz_cam[order], rgb[order]
+    u, v, _ = project_np(q, np.float32)
+    cx = ((u + np.float32(1.0)) / np.float32(2.0)) * np.float32(W - 1)
+    cy = ((v + np.float32(1.0)) / np.float32(2.0)) * np.float32(H - 1)
+    x, y = cx.astype(np.int64), cy.astype(np.int64)
+    img = np.zeros((H, W, 3), dtype=np.float32)
+    yp, ym = np.minimum(y + 1, H - 1), np.maximum(y - 1, 0)
+    xp, xm = np.minimum(x + 1, W - 1), np.maximum(x - 1, 0)
+    for yy, xx in ((y, xm), (y, xp), (ym, xm), (ym, x), (ym, xp), (yp, xm), (yp, x), (yp, xp), (y, x)):
+        img[yy, xx] = col            # numpy fancy assignment: later elements win, like CPU index_put_
+    return img * np.float32(255.0)
+
+
+def _hist512(vals_long):
+    """histogram() of color_utils.py:68-119 with channels [8,8,8] (bin size ceil(255/8)=32), normalised."""
+    b = vals_long // 32
+    idx = b[:, 0] + 8 * b[:, 1] + 64 * b[:, 2]
+    h = np.bincount(idx, minlength=512).astype(np.float32)
+    return h / h.sum()
+
+
+def hist_rerank_scores_np(img, xyz, rgb, poses, num_split_h, num_split_w):
+    """hist_intersect of trim_input_hist_secondary (utils.py:531-579) for K poses, INCLUDING its quirks:
+    only the middle row blocks are compared, the split table is not reset between candidates, and an empty
+    block `break`s the inner loop leaving the remaining columns stale."""
+    img255 = np.asarray(img, dtype=np.float32) * np.float32(255.0)
+    H, W, _ = img255.shape
+    img_mask = ~np.all(img255 == 0, axis=2)
+    bh, bw = H // num_split_h, W // num_split_w
+    split = np.zeros(num_split_h * num_split_w, dtype=np.float32)
+    out = np.zeros(len(poses), dtype=np.float32)
+    xyz = np.asarray(xyz, dtype=np.float32)
+    for i, pose in enumerate(np.asarray(poses, dtype=np.float32)):
+        R = rot_and_derivs_np(pose[3:6], np.float32)[0]
+        q = ((xyz - pose[None, :3]) @ R.T).astype(np.float32)
+        proj = make_pano_np(q, rgb, H, W)
+        proj_mask = ~np.all(proj == 0, axis=2)
+        for h in range(1, num_split_h - 1):
+            for w in range(num_split_w):
+                block = np.zeros((H, W), dtype=bool)
+                block[h * bh:(h + 1) * bh, w * bw:(w + 1) * bw] = True
+                fm, fim = proj_mask & img_mask & block, img_mask & block
+                if fm.sum() == 0 or fim.sum() == 0:
+                    split[h * num_split_w + w] = 0.0
+                    break
+                ph = _hist512(proj[fm].astype(np.int64))
+                ih = _hist512(img255[fim].astype(np.int64))
+                split[h * num_split_w + w] = np.minimum(ih, ph).sum()
+        split[np.isnan(split)] = 0.0
+        out[i] = split.sum() / (num_split_h * num_split_w)
+    return out
+
+
+def hist_rerank_select(scores, num_input):
+    """`argsort()[-num_input:]` flipped (utils.py:583-584): descending intersection."""
+    order = np.argsort(np.asarray(scores), kind="stable")[-num_input:]
+    return order[::-1]

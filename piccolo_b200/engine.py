@@ -139,6 +139,19 @@ def topk(loss: torch.Tensor, k: int) -> torch.Tensor:
     return idx
 
 
+def hist_rerank(cloud: Cloud, img: torch.Tensor, poses: torch.Tensor, num_split_h: int = 4, num_split_w: int = 4) -> torch.Tensor:
+    """`hist_intersect` of trim_input_hist_secondary (utils.py:531-579) for K poses: (K,) float32, larger = better."""
+    lib = _lib.load()
+    _require_cuda(img, "img")
+    p = _poses(poses)
+    img_c = _f32c(img)
+    out = torch.empty(p.shape[0], dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        _lib.check(lib.pcl_hist_rerank(cloud._h, img_c.data_ptr(), int(img_c.shape[0]), int(img_c.shape[1]), p.data_ptr(), p.shape[0],
+                                       int(num_split_h), int(num_split_w), out.data_ptr(), _stream(p.device)))
+    return out
+
+
 class Refiner:
     """Fused refinement of B candidates: every iteration is ONE kernel launch doing loss, backward,
     reduction, Adam, ReduceLROnPlateau and the translation clamp (omniloc.py:44-58, :249-269)."""

@@ -21,26 +21,36 @@ def query_evals(n_points: int, n_grid: int, cfg) -> int:
     return n_points * (n_grid + cfg.num_iter * cfg.num_input)
 
 
-def localize_query(cloud: engine.Cloud, image: engine.Image, grid: torch.Tensor, cfg, timers=None):
+def localize_query(cloud: engine.Cloud, image: engine.Image, grid: torch.Tensor, cfg, timers=None, img: torch.Tensor = None,
+                   num_split=(4, 4)):
     """grid (P,6) start poses on the device.  Returns dict(pose (6,), loss, index, candidates (B,6), losses (B,)).
 
-    Candidate selection: the `num_input` grid poses with the smallest sampling loss.  (The reference
-    inserts a colour-histogram re-rank of the top `num_intermediate` here, utils.py:627 — SURVEY §8f
-    "next" #1; until that kernel lands the top-`num_input` by loss are refined.)"""
+    Candidate selection as `make_input` (utils.py:624-627): the `num_intermediate` grid poses with the smallest
+    sampling loss, re-ranked by colour-histogram intersection down to `num_input`.  The re-rank needs the raw
+    panorama `img` (H,W,3); without it the top-`num_input` by loss are refined directly."""
     ev = timers if timers is not None else {}
-    if "score0" in ev:
-        ev["score0"].record()
+
+    def mark(name):
+        if name in ev:
+            ev[name].record()
+
+    mark("score0")
     loss, _ = engine.score(cloud, image, grid)
-    if "score1" in ev:
-        ev["score1"].record()
-    idx = engine.topk(loss, cfg.num_input)
+    mark("score1")
+    if img is not None:
+        idx = engine.topk(loss, cfg.num_intermediate)
+        mid = grid.index_select(0, idx)
+        scores = engine.hist_rerank(cloud, img, mid, num_split[0], num_split[1])
+        keep = engine.topk(-scores, cfg.num_input)
+        idx = idx.index_select(0, keep)
+    else:
+        idx = engine.topk(loss, cfg.num_input)
+    mark("rerank1")
     starts = grid.index_select(0, idx)
     ref = engine.Refiner(starts.shape[0], cfg.lr, cfg.factor, cfg.patience, bool(cfg.parallel)).reset(starts)
-    if "refine0" in ev:
-        ev["refine0"].record()
+    mark("refine0")
     ref.run(cloud, image, cfg.num_iter)
-    if "refine1" in ev:
-        ev["refine1"].record()
+    mark("refine1")
     out = ref.read()
     best = out["loss"].argmin()
     return {"pose": out["pose"][best], "loss": out["loss"][best], "index": best, "candidates": out["pose"], "losses": out["loss"],
@@ -56,6 +66,6 @@ def localize_query_host(xyz_h: torch.Tensor, rgb_h: torch.Tensor, img_h: torch.T
     grid = grid_h.to(device, non_blocking=True)
     cloud = engine.Cloud(xyz, rgb, cfg.out_of_room_quantile)
     image = engine.Image(img)
-    out = localize_query(cloud, image, grid, cfg)
+    out = localize_query(cloud, image, grid, cfg, img=img)
     res = torch.cat([out["pose"], out["loss"].reshape(1)]).cpu()
     return res[:6], float(res[6])

@@ -71,3 +71,80 @@ def generate_rot_points(init_dict=None, device="cpu") -> torch.Tensor:
             seen.add(key)
             keep.append(i)
     return rot_arr[keep].to(device)
+
+
+def trim_input_hist_secondary(img: torch.Tensor, xyz: torch.Tensor, rgb: torch.Tensor, trans: torch.Tensor, rot: torch.Tensor,
+                              num_input: int, num_split_h: int, num_split_w: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Same contract as the reference (utils.py:510-588): the `num_input` candidates whose rendered colour
+    histograms intersect the query's best, in descending order of intersection."""
+    cloud = engine.get_cloud(xyz, rgb, 0.05)
+    poses = torch.cat([trans.reshape(-1, 3), rot.reshape(-1, 3)], dim=1).to(torch.float32)
+    scores = engine.hist_rerank(cloud, img, poses, num_split_h, num_split_w)
+    order = engine.topk(-scores, min(num_input, scores.numel()))
+    return trans[order], rot[order]
+
+
+def adaptive_trans_num(xyz: torch.Tensor, max_trans_num: int, xy_only: bool = False):
+    """Number of translation start points per axis from the 10-90 % extents (utils.py:282-318)."""
+    from math import ceil
+    ext = (torch.quantile(xyz, dim=0, q=0.90) - torch.quantile(xyz, dim=0, q=0.10)).tolist()
+    if xy_only:
+        return ceil((ext[0] * max_trans_num / ext[1]) ** (1 / 2)), ceil((ext[1] * max_trans_num / ext[0]) ** (1 / 2))
+    n = [ceil((ext[a] ** 2 * max_trans_num / (ext[b] * ext[c])) ** (1 / 3)) for a, b, c in ((0, 1, 2), (1, 0, 2), (2, 0, 1))]
+    return tuple(v - 1 if v % 2 == 0 else v for v in n)
+
+
+def _quantile_any(x: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
+    """torch.quantile refuses inputs above 16M elements; the sort-based equivalent (linear interpolation)."""
+    if x.numel() <= (1 << 24):
+        return torch.quantile(x, q)
+    srt = torch.sort(x).values
+    pos = q.to(torch.float64) * (x.numel() - 1)
+    lo = pos.floor().long()
+    hi = torch.clamp(lo + 1, max=x.numel() - 1)
+    frac = (pos - lo).to(x.dtype)
+    return srt[lo] + (srt[hi] - srt[lo]) * frac
+
+
+def generate_trans_points(xyz: torch.Tensor, init_dict=None, device="cpu") -> torch.Tensor:
+    """Translation start grid (utils.py:363-422): quantile (default) / uniform / manual lattices; pose order =
+    meshgrid 'ij' order flattened, as the reference."""
+    mode = init_dict["trans_init_mode"]
+
+    def axis_points(k, n):
+        ar = torch.arange(n, device=device)
+        if mode == "uniform":
+            return (ar + 1) / (n + 1) * (xyz[:, k].max() - xyz[:, k].min()) + xyz[:, k].min()
+        if mode == "manual":
+            lo, hi = init_dict[("x_min", "y_min", "z_min")[k]], init_dict[("x_max", "y_max", "z_max")[k]]
+            return ar / (n - 1) * (hi - lo) + lo
+        split = (ar + 1) / (n + 1) if 1 / (n + 1) > 0.1 else torch.linspace(0.1, 0.9, n, device=device)
+        return _quantile_any(xyz[:, k], split.to(xyz.dtype))
+
+    if init_dict["xy_only"]:
+        if init_dict["dataset"] not in ("Stanford2D-3D-S", "OmniScenes"):
+            raise NotImplementedError("Other datasets not supported")
+        nx, ny = adaptive_trans_num(xyz, init_dict["num_trans"], xy_only=True)
+        gx, gy = torch.meshgrid(axis_points(0, nx), axis_points(1, ny), indexing="ij")
+        trans = torch.zeros(nx * ny, 3, device=device)
+        trans[:, 0], trans[:, 1] = gx.reshape(-1), gy.reshape(-1)
+        trans[:, 2] = init_dict["z_prior"] if init_dict["z_prior"] is not None else xyz[:, 2].mean()
+        return trans
+    nx, ny, nz = adaptive_trans_num(xyz, init_dict["num_trans"], xy_only=False)
+    gx, gy, gz = torch.meshgrid(axis_points(0, nx), axis_points(1, ny), axis_points(2, nz), indexing="ij")
+    return torch.stack([gx.reshape(-1), gy.reshape(-1), gz.reshape(-1)], dim=1)
+
+
+def make_input(img: torch.Tensor, xyz: torch.Tensor, rgb: torch.Tensor, num_input: int, init_dict=None, criterion: str = "histogram",
+               num_intermediate=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Start-pose selection (utils.py:591-629): rotation grid x translation grid -> loss scoring (top
+    `num_intermediate`) -> colour-histogram re-rank (top `num_input`).  Like the reference, only
+    criterion == 'loss_histogram' is implemented (anything else left `input_trans` unbound there)."""
+    rot = generate_rot_points(init_dict, device=img.device)
+    trans = generate_trans_points(xyz, init_dict, device=img.device)
+    if criterion != "loss_histogram":
+        raise ValueError("only criterion='loss_histogram' is supported (as in the reference, utils.py:625)")
+    if init_dict.get("sample_rate_for_init") is not None:
+        raise NotImplementedError("sample_rate_for_init is broken in the reference (utils.py:618-620 subsamples xyz but not rgb)")
+    trimmed_trans, trimmed_rot = trim_input_loss(img, xyz, rgb, trans, rot, num_intermediate)
+    return trim_input_hist_secondary(img, xyz, rgb, trimmed_trans, trimmed_rot, num_input, init_dict["num_split_h"], init_dict["num_split_w"])

@@ -110,6 +110,24 @@ def main():
                         all_trans=tt_all.numpy(), all_rot=rr_all.numpy())
     print("score_small: best", table.min(), "worst", table.max())
 
+    # ---------------- fixture 2b: histogram re-rank (trim_input_hist_secondary) ------------------
+    sch = synth.make_scene(30000, 128, 256, seed=7)
+    gridh = synth.pose_grid(sch.room, (3, 3, 2), 6)
+    rngh = np.random.default_rng(3)
+    posesh = np.concatenate([gridh[rngh.choice(len(gridh), 20, replace=False)],
+                             (sch.gt_pose + np.array([0.05, -0.04, 0.02, 0.03, 0.01, -0.01]))[None].astype(np.float32),
+                             (sch.gt_pose + np.array([0.4, 0.3, -0.1, 0.3, 0.0, 0.0]))[None].astype(np.float32)]).astype(np.float32)
+    xh, ch, ih = torch.from_numpy(sch.xyz), torch.from_numpy(sch.rgb), torch.from_numpy(sch.img)
+    tr_all, rr_all = ref_utils.trim_input_hist_secondary(ih, xh, ch, torch.from_numpy(posesh[:, :3].copy()), torch.from_numpy(posesh[:, 3:].copy()), len(posesh), 4, 4)
+    tr6, rr6 = ref_utils.trim_input_hist_secondary(ih, xh, ch, torch.from_numpy(posesh[:, :3].copy()), torch.from_numpy(posesh[:, 3:].copy()), 6, 4, 4)
+    Rg = ref_utils.rot_from_ypr(torch.from_numpy(posesh[20, 3:].copy()))
+    pano = ref_utils.make_pano(torch.transpose(torch.matmul(Rg, torch.transpose(xh - torch.from_numpy(posesh[20, :3].copy()), 0, 1)), 0, 1), ch,
+                               resolution=(128, 256), return_torch=True)
+    np.savez_compressed(os.path.join(HERE, "rerank_small.npz"), xyz=sch.xyz, rgb8=sch.rgb8, img8=sch.img8, poses=posesh,
+                        all_trans=tr_all.numpy(), all_rot=rr_all.numpy(), top6_trans=tr6.numpy(), top6_rot=rr6.numpy(),
+                        pano20=pano.numpy())
+    print("rerank_small: best pose", tr6[0].numpy(), "gt", sch.gt_pose[:3])
+
     # ---------------- fixture 3: refinement trajectories (omniloc / omniloc_batch) -------------
     def run_refine(scn, starts, num_iter, tag, factor, early_iter):
         """omniloc per candidate + omniloc_batch in fp32 (the parity target), the same after `early_iter`

@@ -296,3 +296,24 @@ def test_ragged_sizes():
         np.testing.assert_array_equal(count[:5].cpu().numpy(), cnt)
         l1, c1, g1 = engine.loss_fwd_bwd(cloud, image, cu(poses[:1]))
         assert abs(l1.item() - ref[0]) <= LOSS_RTOL * abs(ref[0]) or (np.isnan(ref[0]) and torch.isnan(l1).all())
+
+
+def test_histogram_rerank_matches_reference(golden):
+    """GPU depth-tested splat + block histograms vs trim_input_hist_secondary of the reference."""
+    from piccolo_b200 import engine
+    from piccolo_b200.utils import trim_input_hist_secondary
+    g = golden("rerank_small")
+    rgb, img = synth.rgb_from_u8(g["rgb8"]), synth.img_from_u8(g["img8"])
+    xyz_t, rgb_t, img_t, poses = cu(g["xyz"]), cu(rgb), cu(img), cu(g["poses"])
+    scores = engine.hist_rerank(engine.get_cloud(xyz_t, rgb_t), img_t, poses, 4, 4).cpu().numpy()
+    ref = orc.hist_rerank_scores_np(img, g["xyz"], rgb, g["poses"], 4, 4)
+    np.testing.assert_allclose(scores, ref, atol=2e-3)      # pixel truncation is discontinuous: a few boundary pixels may flip
+    tt, rr = trim_input_hist_secondary(img_t, xyz_t, rgb_t, poses[:, :3], poses[:, 3:], 6, 4, 4)
+    # the reference's own panorama is racy (index_put_ with duplicates): same top-6 SET, best candidate identical
+    ours = {tuple(np.round(np.concatenate([a, b]), 5)) for a, b in zip(tt.cpu().numpy(), rr.cpu().numpy())}
+    theirs = {tuple(np.round(np.concatenate([a, b]), 5)) for a, b in zip(g["top6_trans"], g["top6_rot"])}
+    assert len(ours & theirs) >= 5
+    np.testing.assert_array_equal(tt[0].cpu().numpy(), g["top6_trans"][0])
+    np.testing.assert_array_equal(rr[0].cpu().numpy(), g["top6_rot"][0])
+    again = engine.hist_rerank(engine.get_cloud(xyz_t, rgb_t), img_t, poses, 4, 4).cpu().numpy()
+    np.testing.assert_array_equal(again, scores)             # atomicMax of unique keys: deterministic
