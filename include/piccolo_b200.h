@@ -70,11 +70,12 @@ int64_t pcl_launch_count(void);
 
 /* ---- coloured point cloud ------------------------------------------------------------------ */
 /* xyz_n3_dev, rgb_n3_dev: (N,3) float32.  q: out_of_room_quantile (clamp box = order statistics
- * int(N*q) and int(N*(1-q)) per axis, utils.py:222-227).  Synchronises `stream` before returning. */
+ * int(N*q) and int(N*(1-q)) per axis, utils.py:222-227).  Asynchronous: all work is ordered on `stream`; destroy the
+ * handle only when no work using it is in flight on other streams. */
 int pcl_cloud_create(const float* xyz_n3_dev, const float* rgb_n3_dev, int64_t n, double q, int order,
                      void* stream, pcl_cloud** out);
 int64_t pcl_cloud_size(const pcl_cloud* c);
-/* lo_hi[6] = {x_min, y_min, z_min, x_max, y_max, z_max} (host) */
+/* lo_hi[6] = {x_min, y_min, z_min, x_max, y_max, z_max} (host); the first call blocks on the creation stream */
 int pcl_cloud_bounds(const pcl_cloud* c, float* lo_hi);
 void pcl_cloud_destroy(pcl_cloud* c);
 

@@ -15,6 +15,10 @@
 #define PCL_NSUM 8                // {Σme, Σm, a(3), τ(3)}
 
 void pcl_set_error(const char* fmt, ...);
+// stream-ordered allocations from the device's default memory pool (release threshold raised once so that freed
+// blocks stay cached: creating a cloud / image / refiner per query costs no driver allocation and no device sync)
+cudaError_t pcl_pool_alloc(void** p, size_t bytes, cudaStream_t st);
+void pcl_pool_free(void* p, cudaStream_t st);
 extern std::atomic<long long> g_pcl_launches;
 
 #define PCL_CUDA(expr)                                                                         \
@@ -33,14 +37,18 @@ extern std::atomic<long long> g_pcl_launches;
   } while (0)
 
 struct pcl_cloud {
+  cudaStream_t owner;           // stream the storage is ordered on (freed there)
   float* block;                 // one allocation: x|y|z|r|g|b, each n_pad floats
   float *x, *y, *z, *r, *g, *b;
   int64_t n, n_pad;
-  float lo_hi[6];
+  float* lo_hi_dev;             // clamp box {x,y,z min, x,y,z max} on the device (read by the refine finalize)
+  float lo_hi[6];               // host copy, fetched lazily by pcl_cloud_bounds
+  int lo_hi_valid;
   int order;
 };
 
 struct pcl_image {
+  cudaStream_t owner;
   void* data;
   size_t bytes;
   PclImage view;                // view.data == data
@@ -58,6 +66,8 @@ struct PclRefineState {
 };
 
 struct pcl_refine {
+  cudaStream_t owner;
+  char* block;                  // one allocation: state | evalp | loss | counters
   int B, patience, batch_semantics;
   double lr0, factor;
   PclRefineState* state;        // [B]
@@ -83,7 +93,7 @@ struct PclFinalize {
   float* grad;                  // [P][6]           (GRAD)
   PclRefineState* state;        // [P]              (REFINE)
   float* evalp;                 // [P][6] in/out    (REFINE)
-  float lo[3], hi[3];           // clamp box        (REFINE)
+  const float* box;             // clamp box {lo(3), hi(3)} on the device   (REFINE)
   double factor;
   int patience;
   int batch_semantics;

@@ -81,8 +81,10 @@ extern "C" int pcl_cloud_create(const float* xyz, const float* rgb, int64_t n, d
   c->n = n;
   c->n_pad = (n + PCL_TILE_ALIGN - 1) / PCL_TILE_ALIGN * PCL_TILE_ALIGN;
   c->order = order;
-  PCL_CUDA(cudaMalloc((void**)&c->block, sizeof(float) * 6 * (size_t)c->n_pad));
-  PCL_CUDA(cudaMemsetAsync(c->block, 0, sizeof(float) * 6 * (size_t)c->n_pad, st));
+  c->owner = st;
+  PCL_CUDA(pcl_pool_alloc((void**)&c->block, sizeof(float) * (6 * (size_t)c->n_pad + 8), st));
+  PCL_CUDA(cudaMemsetAsync(c->block, 0, sizeof(float) * (6 * (size_t)c->n_pad + 8), st));
+  c->lo_hi_dev = c->block + 6 * (size_t)c->n_pad;
   c->x = c->block; c->y = c->x + c->n_pad; c->z = c->y + c->n_pad;
   c->r = c->z + c->n_pad; c->g = c->r + c->n_pad; c->b = c->g + c->n_pad;
 
@@ -97,7 +99,7 @@ extern "C" int pcl_cloud_create(const float* xyz, const float* rgb, int64_t n, d
                                     (unsigned int*)nullptr, (unsigned int*)nullptr, (int)n, 0, 63, st);
     const size_t nb = (size_t)n;
     const size_t total = 64 + nb * 8 * 2 + nb * 4 * 2 + tmp_bytes + 256;
-    PCL_CUDA(cudaMalloc(&scratch, total));
+    PCL_CUDA(pcl_pool_alloc(&scratch, total, st));
     char* pch = (char*)scratch;
     mm = (unsigned int*)pch; pch += 64;
     k_in = (unsigned long long*)pch; pch += nb * 8;
@@ -125,18 +127,17 @@ extern "C" int pcl_cloud_create(const float* xyz, const float* rgb, int64_t n, d
     size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (float*)nullptr, (float*)nullptr, (int)n, 0, 32, st);
     void* tmp = nullptr; float* sorted = nullptr;
-    PCL_CUDA(cudaMalloc(&tmp, tmp_bytes + 256));
-    PCL_CUDA(cudaMalloc((void**)&sorted, sizeof(float) * (size_t)n));
+    PCL_CUDA(pcl_pool_alloc(&tmp, tmp_bytes + 256, st));
+    PCL_CUDA(pcl_pool_alloc((void**)&sorted, sizeof(float) * (size_t)n, st));
     const float* axes[3] = {c->x, c->y, c->z};
     for (int k = 0; k < 3; ++k) {
       PCL_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, axes[k], sorted, (int)n, 0, 32, st));
-      PCL_CUDA(cudaMemcpyAsync(&c->lo_hi[k], sorted + i_lo, sizeof(float), cudaMemcpyDeviceToHost, st));
-      PCL_CUDA(cudaMemcpyAsync(&c->lo_hi[3 + k], sorted + i_hi, sizeof(float), cudaMemcpyDeviceToHost, st));
+      PCL_CUDA(cudaMemcpyAsync(c->lo_hi_dev + k, sorted + i_lo, sizeof(float), cudaMemcpyDeviceToDevice, st));
+      PCL_CUDA(cudaMemcpyAsync(c->lo_hi_dev + 3 + k, sorted + i_hi, sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    PCL_CUDA(cudaStreamSynchronize(st));
-    cudaFree(tmp); cudaFree(sorted);
+    pcl_pool_free(tmp, st); pcl_pool_free(sorted, st);
   }
-  if (scratch) cudaFree(scratch);
+  pcl_pool_free(scratch, st);
   *out = c;
   return PCL_OK;
 }
@@ -145,13 +146,19 @@ extern "C" int64_t pcl_cloud_size(const pcl_cloud* c) { return c ? c->n : 0; }
 
 extern "C" int pcl_cloud_bounds(const pcl_cloud* c, float* lo_hi) {
   if (!c || !lo_hi) { pcl_set_error("null cloud or output"); return PCL_ERR_INVALID; }
+  if (!c->lo_hi_valid) {            // first call: one blocking read of the 6 floats
+    pcl_cloud* cc = const_cast<pcl_cloud*>(c);
+    PCL_CUDA(cudaMemcpyAsync(cc->lo_hi, c->lo_hi_dev, sizeof(float) * 6, cudaMemcpyDeviceToHost, c->owner));
+    PCL_CUDA(cudaStreamSynchronize(c->owner));
+    cc->lo_hi_valid = 1;
+  }
   memcpy(lo_hi, c->lo_hi, sizeof(float) * 6);
   return PCL_OK;
 }
 
 extern "C" void pcl_cloud_destroy(pcl_cloud* c) {
   if (!c) return;
-  cudaFree(c->block);
+  pcl_pool_free(c->block, c->owner);
   free(c);
 }
 
@@ -227,14 +234,14 @@ extern "C" int pcl_image_create(const float* img, int h, int w, int format, void
   int fmt = format;
   if (fmt == PCL_IMAGE_AUTO || fmt == PCL_IMAGE_U8Q || fmt == PCL_IMAGE_U8P || fmt == PCL_IMAGE_TEX || fmt == PCL_IMAGE_F16D) {
     int* flag; int host_flag = 0;
-    PCL_CUDA(cudaMalloc((void**)&flag, sizeof(int)));
+    PCL_CUDA(pcl_pool_alloc((void**)&flag, sizeof(int), st));
     PCL_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
     const long long nv = (long long)h * w * 3;
     pcl_u8_exact_kernel<<<(unsigned int)((nv + 255) / 256), 256, 0, st>>>(img, nv, flag);
     PCL_LAUNCH_CHECK();
     PCL_CUDA(cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     PCL_CUDA(cudaStreamSynchronize(st));
-    cudaFree(flag);
+    pcl_pool_free(flag, st);
     if (host_flag) {
       if (fmt != PCL_IMAGE_AUTO) { pcl_set_error("image is not exactly uint8/255: a u8 texel table would change the result"); return PCL_ERR_FORMAT; }
       fmt = PCL_IMAGE_F32;
@@ -249,22 +256,23 @@ extern "C" int pcl_image_create(const float* img, int h, int w, int format, void
     return PCL_ERR_INVALID;
   }
   pcl_image* im = (pcl_image*)calloc(1, sizeof(pcl_image));
+  im->owner = st;
   pcl_image_set_geometry(im->view, h, w, (fmt == PCL_IMAGE_U8Q || fmt == PCL_IMAGE_F16D) ? w + 1 : w + 2);
   im->view.fmt = fmt;
   dim3 block(128), grid((w + 2 + 127) / 128, 1);
   if (fmt == PCL_IMAGE_U8Q) {
     im->bytes = (size_t)(h + 1) * (w + 1) * 16; im->view.tex_scale = 1.0f / 255.0f;
-    PCL_CUDA(cudaMalloc(&im->data, im->bytes));
+    PCL_CUDA(pcl_pool_alloc(&im->data, im->bytes, st));
     grid.y = h + 1;
     pcl_build_u8q_kernel<<<grid, block, 0, st>>>(img, h, w, (uint4*)im->data);
   } else if (fmt == PCL_IMAGE_F16D) {
     im->bytes = (size_t)(h + 1) * (w + 1) * 32; im->view.tex_scale = 1.0f / 255.0f;
-    PCL_CUDA(cudaMalloc(&im->data, im->bytes));
+    PCL_CUDA(pcl_pool_alloc(&im->data, im->bytes, st));
     grid.y = h + 1;
     pcl_build_f16d_kernel<<<grid, block, 0, st>>>(img, h, w, (uint4*)im->data);
   } else if (fmt == PCL_IMAGE_U8P) {
     im->bytes = (size_t)(h + 2) * (w + 2) * 4; im->view.tex_scale = 1.0f / 255.0f;
-    PCL_CUDA(cudaMalloc(&im->data, im->bytes));
+    PCL_CUDA(pcl_pool_alloc(&im->data, im->bytes, st));
     grid.y = h + 2;
     pcl_build_u8p_kernel<<<grid, block, 0, st>>>(img, h, w, (unsigned int*)im->data);
   } else if (fmt == PCL_IMAGE_TEX) {
@@ -272,7 +280,7 @@ extern "C" int pcl_image_create(const float* img, int h, int w, int format, void
     // unnormalised coordinates, normalised-float reads, gather enabled)
     im->bytes = (size_t)h * w * 4; im->view.tex_scale = 1.0f;
     unsigned int* staging;
-    PCL_CUDA(cudaMalloc((void**)&staging, (size_t)(h + 2) * (w + 2) * 4));
+    PCL_CUDA(pcl_pool_alloc((void**)&staging, (size_t)(h + 2) * (w + 2) * 4, st));
     grid.y = h + 2;
     pcl_build_u8p_kernel<<<grid, block, 0, st>>>(img, h, w, staging);
     PCL_LAUNCH_CHECK();
@@ -288,12 +296,12 @@ extern "C" int pcl_image_create(const float* img, int h, int w, int format, void
     cudaTextureObject_t tex = 0;
     PCL_CUDA(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
     PCL_CUDA(cudaStreamSynchronize(st));
-    cudaFree(staging);
+    pcl_pool_free(staging, st);
     im->view.tex = (unsigned long long)tex;
     im->data = (void*)arr;
   } else {
     im->bytes = (size_t)(h + 2) * (w + 2) * 16; im->view.tex_scale = 1.0f;
-    PCL_CUDA(cudaMalloc(&im->data, im->bytes));
+    PCL_CUDA(pcl_pool_alloc(&im->data, im->bytes, st));
     grid.y = h + 2;
     pcl_build_f32_kernel<<<grid, block, 0, st>>>(img, h, w, (float4*)im->data);
   }
@@ -312,7 +320,7 @@ extern "C" void pcl_image_destroy(pcl_image* im) {
     cudaDestroyTextureObject((cudaTextureObject_t)im->view.tex);
     cudaFreeArray((cudaArray_t)im->data);
   } else {
-    cudaFree(im->data);
+    pcl_pool_free(im->data, im->owner);
   }
   free(im);
 }
@@ -337,13 +345,13 @@ extern "C" int pcl_topk(const float* loss, int64_t p, int k, int64_t* idx_k, voi
   const size_t np = (size_t)p;
   const size_t off_tmp = (np * 4 * 2 + np * 8 * 2 + 255) & ~(size_t)255;
   char* buf;
-  PCL_CUDA(cudaMallocAsync((void**)&buf, off_tmp + tmp_bytes + 256, st));
+  PCL_CUDA(pcl_pool_alloc((void**)&buf, off_tmp + tmp_bytes + 256, st));
   float* k_in = (float*)buf; float* k_out = k_in + np;
   long long* v_in = (long long*)(buf + np * 8); long long* v_out = v_in + np;
   pcl_topk_keys_kernel<<<(unsigned int)((p + 255) / 256), 256, 0, st>>>(loss, p, k_in, v_in);
   PCL_LAUNCH_CHECK();
   PCL_CUDA(cub::DeviceRadixSort::SortPairs(buf + off_tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)p, 0, 32, st));
   PCL_CUDA(cudaMemcpyAsync(idx_k, v_out, sizeof(long long) * (size_t)k, cudaMemcpyDeviceToDevice, st));
-  PCL_CUDA(cudaFreeAsync(buf, st));
+  pcl_pool_free(buf, st);
   return PCL_OK;
 }

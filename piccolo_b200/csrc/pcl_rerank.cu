@@ -156,7 +156,7 @@ extern "C" int pcl_hist_rerank(const pcl_cloud* c, const float* img_hw3_dev, int
   const size_t off_ntgt = off_inter + (((size_t)k * nblk * sizeof(float) + 255) & ~(size_t)255);
   const size_t total = off_ntgt + (size_t)k * nblk * sizeof(int);
   char* buf;
-  PCL_CUDA(cudaMallocAsync((void**)&buf, total, st));
+  PCL_CUDA(pcl_pool_alloc((void**)&buf, total, st));
   PCL_CUDA(cudaMemsetAsync(buf, 0, key_bytes, st));
   unsigned long long* keys = (unsigned long long*)buf;
   PclPose* poses = (PclPose*)(buf + off_pose);
@@ -175,6 +175,6 @@ extern "C" int pcl_hist_rerank(const pcl_cloud* c, const float* img_hw3_dev, int
   PCL_LAUNCH_CHECK();
   pcl_rr_final_kernel<<<1, 32, 0, st>>>(inter, n_tgt, n_gt, k, num_split_h, num_split_w, hist_intersect_k_dev);
   PCL_LAUNCH_CHECK();
-  PCL_CUDA(cudaFreeAsync(buf, st));
+  pcl_pool_free(buf, st);
   return PCL_OK;
 }

@@ -32,6 +32,26 @@ void pcl_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* pcl_last_error(void) { return g_err; }
+
+cudaError_t pcl_pool_alloc(void** p, size_t bytes, cudaStream_t st) {
+  static std::atomic<unsigned long long> configured{0};      // bit d set: device d's pool threshold raised
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 64 && !((configured.load() >> dev) & 1ull)) {
+    cudaMemPool_t pool;
+    e = cudaDeviceGetDefaultMemPool(&pool, dev);
+    if (e != cudaSuccess) return e;
+    unsigned long long thr = ~0ull;
+    e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    if (e != cudaSuccess) return e;
+    configured.fetch_or(1ull << dev);
+  }
+  return cudaMallocAsync(p, bytes ? bytes : 1, st);
+}
+void pcl_pool_free(void* p, cudaStream_t st) {
+  if (p) cudaFreeAsync(p, st);
+}
 extern "C" int pcl_abi_version(void) { return PCL_ABI_VERSION; }
 extern "C" int64_t pcl_launch_count(void) { return (int64_t)g_pcl_launches.load(); }
 
@@ -101,7 +121,7 @@ __device__ void pcl_refine_update(PclRefineState& st, float* evalp, const float*
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     float c = newp[i];
-    if (i < 3) c = fminf(fmaxf(c, fin.lo[i]), fin.hi[i]);
+    if (i < 3) c = fminf(fmaxf(c, __ldg(fin.box + i)), __ldg(fin.box + 3 + i));
     st.param[i] = c;
     evalp[i] = fin.batch_semantics ? newp[i] : c;
   }
@@ -328,7 +348,7 @@ static int pcl_run_once(const pcl_cloud* c, const pcl_image* im, const float* po
   double* partial = nullptr;
   unsigned int* counters = nullptr;
   const size_t pbytes = (size_t)pl.gx * pl.NS * (size_t)P * sizeof(double);
-  PCL_CUDA(cudaMallocAsync((void**)&partial, pbytes + (size_t)pl.gy * sizeof(unsigned int), st));
+  PCL_CUDA(pcl_pool_alloc((void**)&partial, pbytes + (size_t)pl.gy * sizeof(unsigned int), st));
   counters = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(partial) + pbytes);
   PCL_CUDA(cudaMemsetAsync(counters, 0, (size_t)pl.gy * sizeof(unsigned int), st));
   PclFinalize fin;
@@ -337,7 +357,7 @@ static int pcl_run_once(const pcl_cloud* c, const pcl_image* im, const float* po
   fin.loss = loss; fin.count = count; fin.grad = grad;
   int rc = bwd ? pcl_launch<true>(pl, c, im, poses, (int)P, partial, counters, fin, st)
                : pcl_launch<false>(pl, c, im, poses, (int)P, partial, counters, fin, st);
-  PCL_CUDA(cudaFreeAsync(partial, st));
+  pcl_pool_free(partial, st);
   return rc;
 }
 
@@ -386,41 +406,48 @@ extern "C" int pcl_refine_create(int b, double lr, double factor, int patience, 
   if (!out || b <= 0 || b > 65536) { pcl_set_error("bad refine batch %d", b); return PCL_ERR_INVALID; }
   pcl_refine* r = (pcl_refine*)calloc(1, sizeof(pcl_refine));
   r->B = b; r->lr0 = lr; r->factor = factor; r->patience = patience; r->batch_semantics = batch_semantics ? 1 : 0;
-  const int gy_max = b;                 // PB >= 1
-  PCL_CUDA(cudaMalloc((void**)&r->state, sizeof(PclRefineState) * b));
-  PCL_CUDA(cudaMalloc((void**)&r->evalp, sizeof(float) * 6 * b));
-  PCL_CUDA(cudaMalloc((void**)&r->loss, sizeof(float) * b));
-  PCL_CUDA(cudaMalloc((void**)&r->counters, sizeof(unsigned int) * gy_max));
-  PCL_CUDA(cudaMemset(r->counters, 0, sizeof(unsigned int) * gy_max));
-  r->partial = nullptr; r->partial_floats = 0;
-  *out = r;
+  *out = r;                          // device storage is allocated by the first pcl_refine_reset, on its stream
   return PCL_OK;
 }
 
 extern "C" int pcl_refine_reset(pcl_refine* r, const float* poses_b6_dev, void* stream) {
   if (!r || !poses_b6_dev) { pcl_set_error("null refine handle or poses"); return PCL_ERR_INVALID; }
-  pcl_refine_reset_kernel<<<(r->B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(r->state, r->evalp, poses_b6_dev, r->B, r->lr0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t b = (size_t)r->B;
+  const size_t o_eval = (sizeof(PclRefineState) * b + 255) & ~(size_t)255;
+  const size_t o_loss = o_eval + ((sizeof(float) * 6 * b + 255) & ~(size_t)255);
+  const size_t o_cnt = o_loss + ((sizeof(float) * b + 255) & ~(size_t)255);
+  if (!r->block) {
+    PCL_CUDA(pcl_pool_alloc((void**)&r->block, o_cnt + sizeof(unsigned int) * b, st));
+    r->owner = st;
+    r->state = (PclRefineState*)r->block;
+    r->evalp = (float*)(r->block + o_eval);
+    r->loss = (float*)(r->block + o_loss);
+    r->counters = (unsigned int*)(r->block + o_cnt);
+  }
+  PCL_CUDA(cudaMemsetAsync(r->counters, 0, sizeof(unsigned int) * b, st));
+  pcl_refine_reset_kernel<<<(r->B + 127) / 128, 128, 0, st>>>(r->state, r->evalp, poses_b6_dev, r->B, r->lr0);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }
 
 extern "C" int pcl_refine_run(pcl_refine* r, const pcl_cloud* c, const pcl_image* im, int num_iter, void* stream) {
-  if (!r) { pcl_set_error("null refine handle"); return PCL_ERR_INVALID; }
+  if (!r || !r->block) { pcl_set_error("refine handle is null or was never reset"); return PCL_ERR_INVALID; }
   int rc = pcl_check_inputs(c, im, r->evalp, r->B);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const PclLaunchPlan pl = pcl_plan(c, r->B, true);
   const size_t need = (size_t)pl.gx * pl.NS * (size_t)r->B;
   if (need > r->partial_floats) {
-    if (r->partial) { PCL_CUDA(cudaStreamSynchronize(st)); PCL_CUDA(cudaFree(r->partial)); }
-    PCL_CUDA(cudaMalloc((void**)&r->partial, need * sizeof(double)));
+    pcl_pool_free(r->partial, st);
+    PCL_CUDA(pcl_pool_alloc((void**)&r->partial, need * sizeof(double), st));
     r->partial_floats = need;
   }
   PclFinalize fin;
   memset(&fin, 0, sizeof(fin));
   fin.mode = PCL_FIN_REFINE;
   fin.loss = r->loss; fin.state = r->state; fin.evalp = r->evalp;
-  for (int i = 0; i < 3; ++i) { fin.lo[i] = c->lo_hi[i]; fin.hi[i] = c->lo_hi[3 + i]; }
+  fin.box = c->lo_hi_dev;
   fin.factor = r->factor; fin.patience = r->patience; fin.batch_semantics = r->batch_semantics;
   for (int it = 0; it < num_iter; ++it) {
     rc = pcl_launch<true>(pl, c, im, r->evalp, r->B, r->partial, r->counters, fin, st);
@@ -431,7 +458,7 @@ extern "C" int pcl_refine_run(pcl_refine* r, const pcl_cloud* c, const pcl_image
 
 extern "C" int pcl_refine_read(const pcl_refine* r, float* pose_b6_dev, float* param_b6_dev, float* loss_b_dev,
                                double* lr_b_dev, void* stream) {
-  if (!r) { pcl_set_error("null refine handle"); return PCL_ERR_INVALID; }
+  if (!r || !r->block) { pcl_set_error("refine handle is null or was never reset"); return PCL_ERR_INVALID; }
   pcl_refine_read_kernel<<<(r->B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(r->state, r->evalp, r->B, r->batch_semantics,
                                                                                 pose_b6_dev, param_b6_dev, loss_b_dev, lr_b_dev);
   PCL_LAUNCH_CHECK();
@@ -440,7 +467,7 @@ extern "C" int pcl_refine_read(const pcl_refine* r, float* pose_b6_dev, float* p
 
 extern "C" void pcl_refine_destroy(pcl_refine* r) {
   if (!r) return;
-  cudaFree(r->state); cudaFree(r->evalp); cudaFree(r->loss); cudaFree(r->counters);
-  if (r->partial) cudaFree(r->partial);
+  pcl_pool_free(r->block, r->owner);
+  pcl_pool_free(r->partial, r->owner);
   free(r);
 }

@@ -49,10 +49,22 @@ class Cloud:
                                             int(order), _stream(self.device), ctypes.byref(h)))
         self._h = h
         self.n = int(xyz_c.shape[0])
-        buf = (ctypes.c_float * 6)()
-        _lib.check(lib.pcl_cloud_bounds(self._h, buf))
-        self.box_lo = torch.tensor(list(buf[:3]), dtype=torch.float32)
-        self.box_hi = torch.tensor(list(buf[3:]), dtype=torch.float32)
+        self._box = None
+
+    def _bounds(self):
+        if self._box is None:                 # lazy: the first read blocks on the creation stream
+            buf = (ctypes.c_float * 6)()
+            _lib.check(_lib.load().pcl_cloud_bounds(self._h, buf))
+            self._box = (torch.tensor(list(buf[:3]), dtype=torch.float32), torch.tensor(list(buf[3:]), dtype=torch.float32))
+        return self._box
+
+    @property
+    def box_lo(self) -> torch.Tensor:
+        return self._bounds()[0]
+
+    @property
+    def box_hi(self) -> torch.Tensor:
+        return self._bounds()[1]
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
