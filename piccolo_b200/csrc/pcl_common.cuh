@@ -69,6 +69,7 @@ struct pcl_refine {
   cudaStream_t owner;
   char* block;                  // one allocation: state | evalp | loss | counters
   int B, patience, batch_semantics;
+  long long steps_done;         // Adam step count so far (identical for all candidates)
   double lr0, factor;
   PclRefineState* state;        // [B]
   float* evalp;                 // [B][6] pose evaluated by the next forward
@@ -95,6 +96,7 @@ struct PclFinalize {
   float* evalp;                 // [P][6] in/out    (REFINE)
   const float* box;             // clamp box {lo(3), hi(3)} on the device   (REFINE)
   double factor;
+  double bc1, bc2_sqrt;         // Adam bias corrections of THIS iteration: 1-0.9^step, sqrt(1-0.999^step)
   int patience;
   int batch_semantics;
 };

@@ -394,8 +394,8 @@ PCL_HD void pcl_finish_gradient(const float* p6, const PclPose& P, const PclImag
   grad6[1] = (float)(-(P.r01 * ax + P.r11 * ay + P.r21 * az));
   grad6[2] = (float)(-(P.r02 * ax + P.r12 * ay + P.r22 * az));
   // dL/dangle = ω·τ with ω_yaw = z, ω_pitch = Rz·y, ω_roll = Rz·Ry·x
-  const double cy = cos((double)p6[3]), sy = sin((double)p6[3]);
-  const double cp = cos((double)p6[4]), sp = sin((double)p6[4]);
+  const double cy = (double)cosf(p6[3]), sy = (double)sinf(p6[3]);    // fp32 trig, like the reference's rotation
+  const double cp = (double)cosf(p6[4]), sp = (double)sinf(p6[4]);
   grad6[3] = (float)tz;
   grad6[4] = (float)(-sy * tx + cy * ty);
   grad6[5] = (float)(cy * cp * tx + sy * cp * ty - sp * tz);

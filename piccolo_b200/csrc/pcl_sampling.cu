@@ -15,6 +15,7 @@
 //           omniloc.py:44-58 / :249-269 (optimiser step, scheduler step, clamp).
 #include "pcl_common.cuh"
 
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -94,10 +95,10 @@ __device__ __forceinline__ int pcl_butterfly_index(const int lane) {
 __device__ void pcl_refine_update(PclRefineState& st, float* evalp, const float* g, float loss, const PclFinalize& fin) {
   st.last_loss = loss;
   st.step += 1;
-  const double bc1 = 1.0 - pow(0.9, (double)st.step);
-  const double bc2 = 1.0 - pow(0.999, (double)st.step);
-  const float step_size = (float)(st.lr / bc1);
-  const float bc2_sqrt = (float)sqrt(bc2);
+  // bias corrections 1 - beta^step are the same for every candidate: computed on the host in fp64 (libm pow, as
+  // python's `beta ** step`) and passed with the launch
+  const float step_size = (float)(st.lr / fin.bc1);
+  const float bc2_sqrt = (float)fin.bc2_sqrt;
   const float w1 = (float)(1.0 - 0.9), b2 = 0.999f, w2 = (float)(1.0 - 0.999);
   float newp[6];
 #pragma unroll
@@ -159,24 +160,32 @@ __device__ __forceinline__ void pcl_process_rows(const PclCloudView& C, const Pc
   }
 }
 
-// HI = 1 compiles for one more resident CTA per SM (forward 4 x 64 regs, forward+backward 3 x 80 regs)
-// instead of (3 x 80, 2 x 128): more warps to hide the texel-gather latency, less ILP inside a thread.
-template <int FMT, bool BWD, int K, int HI>
-__global__ void __launch_bounds__(PCL_THREADS, (BWD ? 2 : 3) + HI)
+// Register budgets: forward 3 CTAs/SM x 80 regs, forward+backward 2 x 128 (one more CTA per SM was measured
+// slower: the lost ILP costs more than the extra warps hide).  Row groups of 4 and 5 rows (K points per thread in
+// registers) tile any range of >= 12 rows exactly, so no CTA falls back to the low-ILP single-row path.
+template <int FMT, bool BWD>
+__global__ void __launch_bounds__(PCL_THREADS, BWD ? 2 : 3)
 pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, const int P, const int PB,
                   const long long n_rows, double* __restrict__ partial, unsigned int* __restrict__ counters, const PclFinalize fin) {
   constexpr int NS = BWD ? PCL_NSUM : 2;
   __shared__ __align__(16) PclPose s_pose[PCL_MAX_POSE_BLOCK];
   __shared__ double s_acc[PCL_WARPS][PCL_MAX_POSE_BLOCK][NS];   // fp64: row-to-row accumulation adds no fp32 error
-  __shared__ double s_sum[PCL_THREADS];
+  __shared__ double2 s_sum[PCL_THREADS];
   __shared__ int s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int p0 = blockIdx.y * PB;
   const int np = min(PB, P - p0);
 
-  if (tid < np) pcl_pose_from_params(poses6 + 6 * (size_t)(p0 + tid), s_pose[tid]);
   for (int i = tid; i < PCL_WARPS * PCL_MAX_POSE_BLOCK * NS; i += PCL_THREADS) (&s_acc[0][0][0])[i] = 0.0;
+#if __CUDA_ARCH__ >= 900
+  // Programmatic dependent launch: this grid may start while the previous launch on the stream (the previous
+  // refinement iteration) is still draining; everything above overlaps with its tail.  The poses written by its
+  // finishing CTA are only read after this wait (no-op when the launch did not opt in).
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+  if (tid < np) pcl_pose_from_params(poses6 + 6 * (size_t)(p0 + tid), s_pose[tid]);
   __syncthreads();
 
   // balanced contiguous row range of this CTA (sizes differ by at most one row of 256 points)
@@ -184,19 +193,25 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
   const long long r_end = n_rows * (long long)(blockIdx.x + 1) / (long long)gridDim.x;
   long long r = r_begin;
   const long long r_full = min(r_end, C.n / PCL_THREADS);      // rows below r_full have 256 real points
-  for (; r + K <= r_full; r += K) pcl_process_rows<FMT, BWD, K, NS, false>(C, I, s_pose, np, s_acc, r, tid, lane, warp);
+  {
+    // n = 4a + b rows (b < 4): b groups of 5 and a-b groups of 4 when a >= b (always for n >= 12)
+    const long long n = r_full - r, a = n >> 2, b = n & 3;
+    long long n5 = (a >= b) ? b : 0, n4 = (a >= b) ? a - b : a;
+    for (; n5 > 0; --n5, r += 5) pcl_process_rows<FMT, BWD, 5, NS, false>(C, I, s_pose, np, s_acc, r, tid, lane, warp);
+    for (; n4 > 0; --n4, r += 4) pcl_process_rows<FMT, BWD, 4, NS, false>(C, I, s_pose, np, s_acc, r, tid, lane, warp);
+  }
   for (; r < r_full; ++r) pcl_process_rows<FMT, BWD, 1, NS, false>(C, I, s_pose, np, s_acc, r, tid, lane, warp);
   for (; r < r_end; ++r) pcl_process_rows<FMT, BWD, 1, NS, true>(C, I, s_pose, np, s_acc, r, tid, lane, warp);
   __syncthreads();
 
-  // CTA partial row: partial[blockIdx.x][s][pose]
+  // CTA partial record: partial[blockIdx.x][pose][s]  (NS contiguous doubles per pose)
   const int nout = np * NS;
   for (int i = tid; i < nout; i += PCL_THREADS) {
-    const int s = i / np, p = i - s * np;
+    const int p = i / NS, s = i - p * NS;
     double t = 0.0;
 #pragma unroll
     for (int w = 0; w < PCL_WARPS; ++w) t += s_acc[w][p][s];
-    partial[((size_t)blockIdx.x * NS + s) * (size_t)P + (size_t)(p0 + p)] = t;
+    partial[((size_t)blockIdx.x * (size_t)P + (size_t)(p0 + p)) * NS + s] = t;
   }
 
   // last-block-done
@@ -210,18 +225,22 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
   if (!s_last) return;
   __threadfence();
 
-  // deterministic two-level reduction of the gridDim.x partial rows: G thread groups stride the rows,
-  // then the groups are summed in fixed order
-  const int G = max(1, PCL_THREADS / nout);
+  // Deterministic two-level reduction of the gridDim.x partial records, latency-optimised: an item is one
+  // 16-byte pair of sums of one pose; G thread groups stride the records with 128-bit L2 loads (16 in flight per
+  // thread), then the groups are summed in fixed order.
+  const int nitems = np * (NS / 2);
+  const int G = max(1, PCL_THREADS / nitems);
   {
-    const int out = tid % nout, g = tid / nout;
-    double t = 0.0;
+    const int item = tid % nitems, g = tid / nitems;
+    double2 t = make_double2(0.0, 0.0);
     if (g < G) {
-      const int s = out / np, p = out - s * np;
-      const double* src = partial + (size_t)s * (size_t)P + (size_t)(p0 + p);
-      const size_t stride = (size_t)NS * (size_t)P;
-#pragma unroll 8
-      for (unsigned int bx = g; bx < gridDim.x; bx += G) t += __ldcg(src + (size_t)bx * stride);
+      const double2* src = reinterpret_cast<const double2*>(partial + (size_t)p0 * NS) + item;
+      const size_t stride = (size_t)P * (NS / 2);
+#pragma unroll 16
+      for (unsigned int bx = g; bx < gridDim.x; bx += G) {
+        const double2 v = __ldcg(src + (size_t)bx * stride);
+        t.x += v.x; t.y += v.y;
+      }
     }
     s_sum[tid] = t;
   }
@@ -229,10 +248,10 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
   if (tid < np) {
     double sums[PCL_NSUM];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      double t = 0.0;
-      for (int g = 0; g < G; ++g) t += s_sum[g * nout + s * np + tid];
-      sums[s] = t;
+    for (int h = 0; h < NS / 2; ++h) {
+      double2 t = make_double2(0.0, 0.0);
+      for (int g = 0; g < G; ++g) { const double2 v = s_sum[g * nitems + tid * (NS / 2) + h]; t.x += v.x; t.y += v.y; }
+      sums[2 * h] = t.x; sums[2 * h + 1] = t.y;
     }
     const int pg = p0 + tid;
     const float* p6 = poses6 + 6 * (size_t)pg;
@@ -255,10 +274,7 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
 // ------------------------------------------------------------------------------------------------
 // host-side launch
 // ------------------------------------------------------------------------------------------------
-#ifndef PCL_DEFAULT_HI
-#define PCL_DEFAULT_HI 0
-#endif
-struct PclLaunchPlan { int K, PB, gx, gy, NS, hi; long long n_rows; };
+struct PclLaunchPlan { int PB, gx, gy, NS; long long n_rows; };
 
 static int pcl_env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -279,12 +295,9 @@ static int pcl_num_sms() {
 // gets an equal share of rows, so there is no tail wave and the last-block reduction reads <= ~450 rows.
 static PclLaunchPlan pcl_plan(const pcl_cloud* c, int64_t P, bool bwd) {
   PclLaunchPlan pl;
-  pl.K = pcl_env_int("PCL_K", 4);
-  if (pl.K != 4 && pl.K != 8) pl.K = 4;
   pl.NS = bwd ? PCL_NSUM : 2;
   pl.n_rows = c->n_pad / PCL_THREADS;
-  pl.hi = pcl_env_int(bwd ? "PCL_OCC_BWD" : "PCL_OCC_FWD", PCL_DEFAULT_HI) ? 1 : 0;
-  const int resident = pcl_num_sms() * ((bwd ? 2 : 3) + pl.hi);
+  const int resident = pcl_num_sms() * (bwd ? 2 : 3);
   // pose block: as many poses per CTA as possible (point loads amortise over the block) while leaving
   // enough CTAs to fill the machine
   int PB = (int)(P < PCL_MAX_POSE_BLOCK ? P : PCL_MAX_POSE_BLOCK);
@@ -308,28 +321,36 @@ static PclLaunchPlan pcl_plan(const pcl_cloud* c, int64_t P, bool bwd) {
 }
 
 template <int FMT, bool BWD>
-static void pcl_launch_fmt(const PclLaunchPlan& pl, const PclCloudView& C, const PclImage& I, const float* poses, int P,
-                           double* partial, unsigned int* counters, const PclFinalize& fin, cudaStream_t st) {
-  dim3 grid(pl.gx, pl.gy), block(PCL_THREADS);
-#define PCL_GO(KK, HH) pcl_sample_kernel<FMT, BWD, KK, HH><<<grid, block, 0, st>>>(C, I, poses, P, pl.PB, pl.n_rows, partial, counters, fin)
-  if (pl.hi) { if (pl.K == 8) PCL_GO(8, 1); else PCL_GO(4, 1); }
-  else { if (pl.K == 8) PCL_GO(8, 0); else PCL_GO(4, 0); }
-#undef PCL_GO
+static cudaError_t pcl_launch_fmt(const PclLaunchPlan& pl, const PclCloudView& C, const PclImage& I, const float* poses, int P,
+                                  double* partial, unsigned int* counters, const PclFinalize& fin, cudaStream_t st, bool pdl) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(pl.gx, pl.gy);
+  cfg.blockDim = dim3(PCL_THREADS);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, pcl_sample_kernel<FMT, BWD>, C, I, poses, P, pl.PB, pl.n_rows, partial, counters, fin);
 }
 
 template <bool BWD>
 static int pcl_launch(const PclLaunchPlan& pl, const pcl_cloud* c, const pcl_image* im, const float* poses, int P,
-                      double* partial, unsigned int* counters, const PclFinalize& fin, cudaStream_t st) {
+                      double* partial, unsigned int* counters, const PclFinalize& fin, cudaStream_t st, bool pdl = false) {
   PclCloudView C = {c->x, c->y, c->z, c->r, c->g, c->b, (long long)c->n};
+  cudaError_t e;
   switch (im->view.fmt) {
-    case PCL_FMT_U8Q: pcl_launch_fmt<PCL_FMT_U8Q, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st); break;
-    case PCL_FMT_U8P: pcl_launch_fmt<PCL_FMT_U8P, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st); break;
-    case PCL_FMT_F32: pcl_launch_fmt<PCL_FMT_F32, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st); break;
-    case PCL_FMT_TEX: pcl_launch_fmt<PCL_FMT_TEX, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st); break;
-    case PCL_FMT_F16D: pcl_launch_fmt<PCL_FMT_F16D, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st); break;
+    case PCL_FMT_U8Q: e = pcl_launch_fmt<PCL_FMT_U8Q, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st, pdl); break;
+    case PCL_FMT_U8P: e = pcl_launch_fmt<PCL_FMT_U8P, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st, pdl); break;
+    case PCL_FMT_F32: e = pcl_launch_fmt<PCL_FMT_F32, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st, pdl); break;
+    case PCL_FMT_TEX: e = pcl_launch_fmt<PCL_FMT_TEX, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st, pdl); break;
+    case PCL_FMT_F16D: e = pcl_launch_fmt<PCL_FMT_F16D, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st, pdl); break;
     default: pcl_set_error("unknown image format %d", im->view.fmt); return PCL_ERR_INVALID;
   }
-  PCL_LAUNCH_CHECK();
+  g_pcl_launches.fetch_add(1);
+  PCL_CUDA(e);
   return PCL_OK;
 }
 
@@ -426,6 +447,7 @@ extern "C" int pcl_refine_reset(pcl_refine* r, const float* poses_b6_dev, void* 
     r->counters = (unsigned int*)(r->block + o_cnt);
   }
   PCL_CUDA(cudaMemsetAsync(r->counters, 0, sizeof(unsigned int) * b, st));
+  r->steps_done = 0;
   pcl_refine_reset_kernel<<<(r->B + 127) / 128, 128, 0, st>>>(r->state, r->evalp, poses_b6_dev, r->B, r->lr0);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
@@ -450,7 +472,11 @@ extern "C" int pcl_refine_run(pcl_refine* r, const pcl_cloud* c, const pcl_image
   fin.box = c->lo_hi_dev;
   fin.factor = r->factor; fin.patience = r->patience; fin.batch_semantics = r->batch_semantics;
   for (int it = 0; it < num_iter; ++it) {
-    rc = pcl_launch<true>(pl, c, im, r->evalp, r->B, r->partial, r->counters, fin, st);
+    r->steps_done += 1;
+    fin.bc1 = 1.0 - pow(0.9, (double)r->steps_done);
+    fin.bc2_sqrt = sqrt(1.0 - pow(0.999, (double)r->steps_done));
+    // iterations after the first opt in to programmatic dependent launch (prologue overlaps the previous tail)
+    rc = pcl_launch<true>(pl, c, im, r->evalp, r->B, r->partial, r->counters, fin, st, it > 0 && pcl_env_int("PCL_PDL", 1) != 0);
     if (rc) return rc;
   }
   return PCL_OK;

@@ -48,27 +48,26 @@ def main():
         cloud = engine.Cloud(xyz, rgb, 0.05, order)
         for fmt in FMTS:
             image = engine.Image(img, fmt)
-            for K, occ in ((4, 0), (4, 1), (8, 0)):
-                os.environ["PCL_K"] = str(K); os.environ["PCL_OCC_FWD"] = str(occ); os.environ["PCL_OCC_BWD"] = str(occ)
-                ms = timeit(lambda: engine.score(cloud, image, poses))
-                print(f"order={order} fmt={fmt} K={K} occ={occ} SCORE P={len(poses)}: {ms:.3f} ms  {len(poses)*N/ms/1e6:.1f} G pp/s", flush=True)
-                ms = timeit(lambda: engine.loss_fwd_bwd(cloud, image, cand), iters=20, warm=3)
-                print(f"order={order} fmt={fmt} K={K} occ={occ} FWDBWD B=6: {ms:.4f} ms  {6*N/ms/1e6:.1f} G pp/s", flush=True)
-                c64 = cand.repeat(11, 1)[:64].contiguous()
-                ms = timeit(lambda: engine.loss_fwd_bwd(cloud, image, c64), iters=10, warm=2)
-                print(f"order={order} fmt={fmt} K={K} occ={occ} FWDBWD B=64: {ms:.4f} ms  {64*N/ms/1e6:.1f} G pp/s", flush=True)
+            ms = timeit(lambda: engine.score(cloud, image, poses))
+            print(f"order={order} fmt={fmt} SCORE P={len(poses)}: {ms:.3f} ms  {len(poses)*N/ms/1e6:.1f} G pp/s", flush=True)
+            ms = timeit(lambda: engine.loss_fwd_bwd(cloud, image, cand), iters=20, warm=3)
+            print(f"order={order} fmt={fmt} FWDBWD B=6: {ms:.4f} ms  {6*N/ms/1e6:.1f} G pp/s", flush=True)
+            c64 = cand.repeat(11, 1)[:64].contiguous()
+            ms = timeit(lambda: engine.loss_fwd_bwd(cloud, image, c64), iters=10, warm=2)
+            print(f"order={order} fmt={fmt} FWDBWD B=64: {ms:.4f} ms  {64*N/ms/1e6:.1f} G pp/s", flush=True)
             if order == 0:
                 break
     # large-batch fwd+bwd (amortises launch + tail): 64 candidates
-    os.environ["PCL_K"] = "4"; os.environ["PCL_OCC_FWD"] = "0"; os.environ["PCL_OCC_BWD"] = "0"
     cloud = engine.Cloud(xyz, rgb, 0.05, 1)
-    image = engine.Image(img, "u8q")
+    image = engine.Image(img)
     cand64 = cand.repeat(11, 1)[:64].contiguous()
     ms = timeit(lambda: engine.loss_fwd_bwd(cloud, image, cand64), iters=10)
-    print(f"FWDBWD B=64 u8q K=4: {ms:.3f} ms {64*N/ms/1e6:.1f} G pp/s")
+    print(f"FWDBWD B=64 auto: {ms:.3f} ms {64*N/ms/1e6:.1f} G pp/s")
     ref = engine.Refiner(6, 0.1, 0.8, 5, True).reset(cand)
-    ms = timeit(lambda: ref.run(cloud, image, 100), iters=3, warm=1)
-    print(f"REFINE 100 iters B=6: {ms:.2f} ms  -> {ms/100*1000:.1f} us/iter, {600*N/ms/1e6:.1f} G pp/s")
+    for pdl in ("1", "0"):
+        os.environ["PCL_PDL"] = pdl
+        ms = timeit(lambda: ref.run(cloud, image, 100), iters=3, warm=1)
+        print(f"REFINE 100 iters B=6 pdl={pdl}: {ms:.2f} ms  -> {ms/100*1000:.1f} us/iter, {600*N/ms/1e6:.1f} G pp/s")
 
 
 if __name__ == "__main__":

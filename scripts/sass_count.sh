@@ -1,8 +1,8 @@
 #!/bin/bash
-# Instruction count of the K=4 pose loop (per evaluation) of the u8q scoring and fwd+bwd kernels.
+# Instruction count of the pose loops (K=4 and K=5 row groups) of the f16d scoring and fwd+bwd kernels.
 O=/root/repo/piccolo_b200/csrc/pcl_sampling.o
-for k in "${@:-ILi1ELb0ELi4ELi0 ILi1ELb1ELi4ELi0}"; do for kk in $k; do
-cuobjdump -sass -fun "_Z17pcl_sample_kernel${kk}EEv12PclCloudView8PclImagePKfiixPdPj11PclFinalize" $O | grep -E "^\s+/\*[0-9a-f]{4}\*/" > /tmp/w/k_$kk.sass
+for k in "${@:-ILi5ELb0E ILi5ELb1E}"; do for kk in $k; do
+cuobjdump -sass -fun "_Z17pcl_sample_kernel${kk}Ev12PclCloudView8PclImagePKfiixPdPj11PclFinalize" $O | grep -E "^\s+/\*[0-9a-f]{4}\*/" > /tmp/w/k_$kk.sass
 python - "$kk" <<'PY'
 import re,sys,collections
 kk=sys.argv[1]
@@ -19,6 +19,6 @@ for i,l in enumerate(lines):
                 for a,ll in zip(addr,lines):
                     if t<=a<=addr[i]:
                         mm=re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)",ll); c[mm.group(1)]+=1
-                print(kk,"K=4 pose loop:",n,"->",n/4,"per eval", sorted(c.items(), key=lambda x:-x[1])[:14])
+                print(kk,"pose loop:",n,"instr (K=4: /4, K=5: /5 per eval)", sorted(c.items(), key=lambda x:-x[1])[:14])
 PY
 done; done
