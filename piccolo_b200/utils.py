@@ -148,3 +148,43 @@ def make_input(img: torch.Tensor, xyz: torch.Tensor, rgb: torch.Tensor, num_inpu
         raise NotImplementedError("sample_rate_for_init is broken in the reference (utils.py:618-620 subsamples xyz but not rgb)")
     trimmed_trans, trimmed_rot = trim_input_loss(img, xyz, rgb, trans, rot, num_intermediate)
     return trim_input_hist_secondary(img, xyz, rgb, trimmed_trans, trimmed_rot, num_input, init_dict["num_split_h"], init_dict["num_split_w"])
+
+
+def out_of_room(xyz: torch.Tensor, trans: torch.Tensor, out_quantile: float = 0.05) -> bool:
+    """True if `trans` (3,1) lies outside the out_quantile box of the cloud (utils.py:232-254)."""
+    with torch.no_grad():
+        for k in range(3):
+            lo, hi = quantile(xyz[:, k], out_quantile)
+            if not (lo < trans[k][0] < hi):
+                return True
+    return False
+
+
+def make_pano(xyz: torch.Tensor, rgb: torch.Tensor, resolution=(200, 400), return_torch: bool = False):
+    """Painter's-algorithm render of camera-frame points to an equirectangular image (utils.py:134-205), used for
+    the result PNGs.  Deterministic version of the reference's nine `index_put_` calls: nearest point wins, the
+    centre write beats the 3x3 dilation writes."""
+    from .omniloc import _rotation_from_angles  # noqa: F401  (keeps import graph identical on CPU-only machines)
+    import numpy as np
+    H, W = resolution
+    with torch.no_grad():
+        q = xyz.detach().to(torch.float32).cpu()
+        col = rgb.detach().to(torch.float32).cpu()
+        dist = torch.linalg.vector_norm(q, dim=-1)
+        order = torch.argsort(dist, descending=True, stable=True)
+        q, col = q[order], col[order]
+        theta = torch.atan2(torch.linalg.vector_norm(q[:, :2], dim=-1), q[:, 2] + 1e-6)
+        phi = torch.atan2(q[:, 1], q[:, 0] + 1e-6) + np.pi
+        u, v = 2 * (1.0 - phi / (2 * np.pi)) - 1, 2 * (theta / np.pi) - 1
+        x = (((u + 1.0) / 2.0) * (W - 1)).long()
+        y = (((v + 1.0) / 2.0) * (H - 1)).long()
+        image = torch.zeros(H * W, 3)
+        yp, ym, xp, xm = (y + 1).clamp(max=H - 1), (y - 1).clamp(min=0), (x + 1).clamp(max=W - 1), (x - 1).clamp(min=0)
+        rank = torch.arange(len(q))
+        best = torch.full((H * W,), -1, dtype=torch.long)
+        for call, (yy, xx) in enumerate(((y, xm), (y, xp), (ym, xm), (ym, x), (ym, xp), (yp, xm), (yp, x), (yp, xp), (y, x))):
+            best.scatter_reduce_(0, yy * W + xx, call * len(q) + rank, reduce="amax")   # later call, nearer point wins
+        hit = best >= 0
+        image[hit] = col[best[hit] % len(q)]
+        image = image.reshape(H, W, 3) * 255
+        return image if return_torch else image.numpy().astype(np.uint8)

@@ -129,3 +129,30 @@ def test_c4_shapes_multi_query_perturbed():
         assert torch.isfinite(out["losses"]).all()
     ok = [t < 0.1 and r < 5.0 for t, r in results]                          # omniscenes success thresholds (localize.py:513)
     assert sum(ok) >= 2, results
+
+
+def test_main_cli_writes_reference_outputs(tmp_path):
+    """`python main.py --config configs/stanford_parallel.ini --log DIR --override ...` on the synthetic dataset:
+    config.ini, stanford_results.csv with the reference's header/row shape, TensorBoard event file, result PNG."""
+    import csv
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    log = str(tmp_path / "log")
+    ov = "synthetic_points=120000,synthetic_queries=2,synthetic_height=256,num_iter=60,sharpen_color=False"
+    r = subprocess.run([sys.executable, os.path.join(root, "main.py"), "--config", os.path.join(root, "configs", "stanford_parallel.ini"),
+                        "--log", log, "--override", ov], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert os.path.exists(os.path.join(log, "config.ini"))
+    rows = list(csv.reader(open(os.path.join(log, "stanford_results.csv"))))
+    assert rows[0] == ["area_num", "pano_name", "gt_trans", "gt_rot", "skipped?", "OmniLoc_trans", "OmniLoc_rot", "t_error (m)", "r_error (degrees)", "time (s)"]
+    assert len(rows) == 3
+    for row in rows[1:]:
+        assert len(row) in (5, 10)
+        if len(row) == 10:
+            assert row[4] == "0" and len(row[5].split()) == 3 and len(row[6].split()) == 9 and float(row[9]) > 0
+    assert any(f.startswith("events.out.tfevents") for f in os.listdir(log))
+    assert "Final Accuracy" in r.stdout and "current accuracy" in r.stdout
+    pngs = [f for _, _, fs in os.walk(os.path.join(log, "results")) for f in fs if f.endswith(".png")]
+    assert len(pngs) >= 1

@@ -1,0 +1,78 @@
+"""CPU tests of the host-side mirror of the reference interface: config parsing, colour preprocessing,
+candidate grids, the torch make_pano used for result images."""
+import os
+
+import numpy as np
+import torch
+
+from piccolo_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_configs_parse_to_reference_values():
+    from piccolo_b200.parse_utils import apply_override, parse_ini, parse_override, parse_value, save_effective_config
+    cfg = parse_ini(os.path.join(ROOT, "configs", "stanford.ini"))
+    assert cfg.dataset == "Stanford2D-3D-S" and cfg.num_trans == 50 and cfg.num_yaw == 4 and cfg.factor == 0.8
+    assert cfg.area is None and cfg.sharpen_color is True and cfg.visualize is False and cfg.criterion == "loss_histogram"
+    par = parse_ini(os.path.join(ROOT, "configs", "stanford_parallel.ini"))
+    assert par.parallel is True and par.sample_rate == 6
+    omni = parse_ini(os.path.join(ROOT, "configs", "omniscenes.ini"))
+    assert omni.xy_only and omni.yaw_only and omni.z_prior == 1.5 and omni.num_trans == 150 and omni.match_color
+    assert parse_value("1e-3") == 1e-3 and parse_value("None") is None and parse_value("a, b") == ["a", "b"]
+    ov = parse_override("lr=0.05,room_name=a,b,num_iter=10")
+    assert ov == {"lr": 0.05, "room_name": ["a", "b"], "num_iter": 10}
+    cfg2 = apply_override(cfg, ov)
+    assert cfg2.lr == 0.05 and cfg2.num_iter == 10 and cfg2.room_name == ["a", "b"] and cfg2.patience == 5
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        save_effective_config(cfg2, os.path.join(d, "config.ini"))
+        back = parse_ini(os.path.join(d, "config.ini"))
+        assert back.lr == 0.05 and back.num_iter == 10 and back.dataset == cfg.dataset and back.area is None
+
+
+def test_colour_preprocessing_matches_reference(golden):
+    from piccolo_b200.color_utils import color_match, color_mod
+    g = golden("color_small")
+    img = torch.from_numpy(synth.img_from_u8(g["img8"]))
+    rgb = torch.from_numpy(synth.rgb_from_u8(g["rgb8"]))
+    a_img, a_rgb = color_mod(img.clone(), rgb.clone(), 256)
+    np.testing.assert_array_equal(a_img.numpy(), g["mod_img"])
+    np.testing.assert_array_equal(a_rgb.numpy(), g["mod_rgb"])
+    m = color_match(img.clone(), rgb.clone())
+    np.testing.assert_allclose(m.numpy(), g["match_img"], atol=2e-6)
+    assert ((255 * m.numpy()).astype(np.uint8) != (255 * g["match_img"]).astype(np.uint8)).mean() < 1e-3
+
+
+def test_candidate_grids():
+    from piccolo_b200.localize import get_init_dict
+    from piccolo_b200.parse_utils import parse_ini
+    from piccolo_b200.utils import adaptive_trans_num, generate_rot_points, generate_trans_points, grid_poses
+    sc = synth.make_scene(50_000, 32, 64, seed=2)
+    xyz = torch.from_numpy(sc.xyz)
+    init = get_init_dict(parse_ini(os.path.join(ROOT, "configs", "stanford.ini")))
+    rot = generate_rot_points(init)
+    assert rot.shape == (24, 3)                                            # 24 of the 64 Euler triples are distinct rotations
+    assert adaptive_trans_num(xyz, 50) == (5, 5, 3)                        # 8 x 6 x 3 m room
+    trans = generate_trans_points(xyz, init)
+    assert trans.shape == (75, 3)
+    lo, hi = torch.quantile(xyz, 0.1, dim=0), torch.quantile(xyz, 0.9, dim=0)
+    assert (trans >= lo - 1e-4).all() and (trans <= hi + 1e-4).all()
+    poses = grid_poses(trans, rot)
+    assert poses.shape == (1800, 6) and torch.equal(poses[25, :3], trans[1]) and torch.equal(poses[25, 3:], rot[1])
+    omni = get_init_dict(parse_ini(os.path.join(ROOT, "configs", "omniscenes.ini")))
+    t2, r2 = generate_trans_points(xyz, omni), generate_rot_points(omni)
+    assert r2.shape == (8, 3) and (r2[:, 1:] == 0).all() and (t2[:, 2] == 1.5).all() and t2.shape[0] >= 150
+
+
+def test_make_pano_matches_oracle_painter_order():
+    from oracle import piccolo_oracle as orc
+    from piccolo_b200.utils import make_pano
+    sc = synth.make_scene(20_000, 32, 64, seed=4)
+    pose = sc.gt_pose.astype(np.float32)
+    R = orc.rot_and_derivs_np(pose[3:6], np.float32)[0]
+    q = ((sc.xyz - pose[None, :3]) @ R.T).astype(np.float32)
+    ours = make_pano(torch.from_numpy(q), torch.from_numpy(sc.rgb), resolution=(64, 128), return_torch=True).numpy()
+    ref = orc.make_pano_np(q, sc.rgb, 64, 128)
+    np.testing.assert_array_equal(ours.sum(2) > 0, ref.sum(2) > 0)
+    assert (np.abs(ours - ref).max(axis=2) > 0).mean() < 5e-3             # atan2 ulps at pixel-truncation boundaries
