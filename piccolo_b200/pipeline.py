@@ -69,3 +69,30 @@ def localize_query_host(xyz_h: torch.Tensor, rgb_h: torch.Tensor, img_h: torch.T
     out = localize_query(cloud, image, grid, cfg, img=img)
     res = torch.cat([out["pose"], out["loss"].reshape(1)]).cpu()
     return res[:6], float(res[6])
+
+
+def localize_query_sharded(cloud: engine.Cloud, image: engine.Image, grid: torch.Tensor, cfg, img: torch.Tensor = None, num_split=(4, 4)):
+    """ONE query sharded over the ranks of the default process group (config C3): each rank scores a contiguous
+    slice of the pose grid, the per-pose losses are all-gathered (NCCL, KB-sized), every rank runs the same
+    deterministic top-K / re-rank, the surviving candidates are dealt round-robin for refinement and the
+    (loss, pose) rows are all-gathered before the arg-min.  Cloud and panorama are replicated on every GPU.
+    Returns the same dict as `localize_query` on every rank."""
+    from . import dist as pdist
+    loss = pdist.score_sharded(lambda p: engine.score(cloud, image, p)[0], grid)
+    if img is not None:
+        idx = engine.topk(loss, cfg.num_intermediate)
+        mid = grid.index_select(0, idx)
+        keep = engine.topk(-engine.hist_rerank(cloud, img, mid, num_split[0], num_split[1]), cfg.num_input)
+        idx = idx.index_select(0, keep)
+    else:
+        idx = engine.topk(loss, cfg.num_input)
+    starts = grid.index_select(0, idx)
+
+    def refine_fn(s):
+        ref = engine.Refiner(s.shape[0], cfg.lr, cfg.factor, cfg.patience, bool(cfg.parallel)).reset(s)
+        out = ref.run(cloud, image, cfg.num_iter).read()
+        return torch.cat([out["loss"].reshape(-1, 1), out["pose"]], dim=1)
+
+    table = pdist.refine_sharded(refine_fn, starts)
+    k, pose, best = pdist.argmin_candidate(table)
+    return {"pose": pose, "loss": best, "index": k, "candidates": table[:, 1:], "losses": table[:, 0], "start_index": idx, "grid_loss": loss}

@@ -1,0 +1,47 @@
+"""One C3-shaped query sharded over all ranks (launch with torchrun); rank 0 also runs it unsharded and checks
+that the sharded run selects the same candidates and finds the same pose.
+    python -m torch.distributed.run --nproc-per-node N scripts/run_sharded_query.py [n_points] [height] [grid_side]"""
+import os, sys, time
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from piccolo_b200 import engine, pipeline, synth
+
+rank, local, ws = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if ws > 1:
+    dist.init_process_group("nccl", device_id=dev)
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+H = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+side = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+room = (40.0, 30.0, 3.0)
+sc = synth.make_scene(N, H, 2 * H, room=room, seed=5)
+grid_np = synth.pose_grid(room, (side, side, 1), 16)
+gt = sc.gt_pose.copy()
+near = grid_np[np.argmin(np.linalg.norm(grid_np[:, :3] - gt[:3], axis=1) + 10 * np.abs(((grid_np[:, 3] - gt[3] + np.pi) % (2 * np.pi)) - np.pi))]
+xyz, rgb, img, grid = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (sc.xyz, sc.rgb, sc.img, grid_np)]
+cloud, image = engine.Cloud(xyz, rgb), engine.Image(img)
+cfg = pipeline.STANFORD_PARALLEL
+out = pipeline.localize_query_sharded(cloud, image, grid, cfg, img=img)       # warm-up
+torch.cuda.synchronize()
+if ws > 1:
+    dist.barrier()
+t0 = time.perf_counter()
+out = pipeline.localize_query_sharded(cloud, image, grid, cfg, img=img)
+torch.cuda.synchronize()
+if ws > 1:
+    dist.barrier()
+dt = time.perf_counter() - t0
+if rank == 0:
+    pose = out["pose"].cpu().numpy()
+    single = pipeline.localize_query(cloud, image, grid, cfg, img=img)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter(); single = pipeline.localize_query(cloud, image, grid, cfg, img=img); torch.cuda.synchronize(); dt1 = time.perf_counter() - t1
+    same_starts = bool(torch.equal(torch.sort(single["start_index"]).values, torch.sort(out["start_index"]).values))
+    dpos = float(np.linalg.norm(pose[:3] - single["pose"].cpu().numpy()[:3]))
+    evals = pipeline.query_evals(N, grid.shape[0], cfg)
+    print(f"ranks={ws} N={N} pano={H}x{2*H} grid={grid.shape[0]}: sharded {dt*1e3:.1f} ms/query ({evals/dt/1e9:.1f} G pp/s) vs single-GPU {dt1*1e3:.1f} ms; "
+          f"same candidate set={same_starts}; |t_sharded - t_single|={dpos*1e3:.2f} mm; t_err vs GT {np.linalg.norm(pose[:3]-gt[:3])*1e3:.1f} mm; format={image.format}")
+    assert same_starts and dpos < 0.01
+if ws > 1:
+    dist.destroy_process_group()
