@@ -256,9 +256,16 @@ template <int FMT>
 PCL_HD void pcl_fetch_basis(const PclImage& I, unsigned int idx, float x0f, float y0f, PclBasis& b) {
   if (FMT == PCL_FMT_F16D) {
     // 32-byte entry per footprint: for each channel the four basis values as fp16 (exact small integers):
-    // two 128-bit loads from one 32-byte sector, one conversion per value, no differences to form
+    // one 256-bit load (one 32-byte sector), one conversion per value, no differences to form
     const pcl_u4* e = reinterpret_cast<const pcl_u4*>(I.data) + 2 * (size_t)idx;
-    const pcl_u4 lo = PCL_LDG128(e), hi = PCL_LDG128(e + 1);
+    pcl_u4 lo, hi;
+#if defined(__CUDA_ARCH__)
+    // sm_100 256-bit load (LDG.E.ENL2.256): the whole 32-byte entry in ONE request per lane
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(e));
+#else
+    lo = PCL_LDG128(e); hi = PCL_LDG128(e + 1);
+#endif
     b.nw[0] = pcl_half_lo(lo.x); b.dxt[0] = pcl_half_hi(lo.x); b.dy0[0] = pcl_half_lo(lo.y); b.ddx[0] = pcl_half_hi(lo.y);
     b.nw[1] = pcl_half_lo(lo.z); b.dxt[1] = pcl_half_hi(lo.z); b.dy0[1] = pcl_half_lo(lo.w); b.ddx[1] = pcl_half_hi(lo.w);
     b.nw[2] = pcl_half_lo(hi.x); b.dxt[2] = pcl_half_hi(hi.x); b.dy0[2] = pcl_half_lo(hi.y); b.ddx[2] = pcl_half_hi(hi.y);
