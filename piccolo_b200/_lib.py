@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpiccolo_b200.so")
+LIB_PATH = os.environ.get("PCL_LIB", os.path.join(_HERE, "libpiccolo_b200.so"))   # PCL_LIB: A/B testing of builds
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
 c_void_pp = ctypes.POINTER(ctypes.c_void_p)
