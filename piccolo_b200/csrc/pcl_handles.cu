@@ -74,7 +74,7 @@ __global__ void pcl_gather_kernel(const float* __restrict__ xyz, const float* __
 }
 
 extern "C" int pcl_cloud_create(const float* xyz, const float* rgb, int64_t n, double q, int order, void* stream, pcl_cloud** out) {
-  if (!xyz || !rgb || !out || n <= 0 || n > 0xfffffff0ll) { pcl_set_error("bad cloud arguments (n=%lld)", (long long)n); return PCL_ERR_INVALID; }
+  if (!xyz || !rgb || !out || n <= 0 || n > 0x7fffff00ll) { pcl_set_error("bad cloud arguments (n=%lld)", (long long)n); return PCL_ERR_INVALID; }
   if (!(q >= 0.0 && q <= 1.0)) { pcl_set_error("quantile %g outside [0,1]", q); return PCL_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
   pcl_cloud* c = (pcl_cloud*)calloc(1, sizeof(pcl_cloud));

@@ -356,7 +356,7 @@ static int pcl_launch(const PclLaunchPlan& pl, const pcl_cloud* c, const pcl_ima
 
 static int pcl_check_inputs(const pcl_cloud* c, const pcl_image* im, const void* poses, int64_t P) {
   if (!c || !im || !poses) { pcl_set_error("null handle or pose pointer"); return PCL_ERR_INVALID; }
-  if (P <= 0 || P > (1 << 24)) { pcl_set_error("pose count %lld out of range", (long long)P); return PCL_ERR_INVALID; }
+  if (P <= 0 || P > 65535ll * PCL_MAX_POSE_BLOCK) { pcl_set_error("pose count %lld out of range (1 .. %lld)", (long long)P, 65535ll * PCL_MAX_POSE_BLOCK); return PCL_ERR_INVALID; }
   return PCL_OK;
 }
 
