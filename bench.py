@@ -48,6 +48,15 @@ def measured_hbm_peak():
         return 6650.0, "fallback"
 
 
+def ncu_traffic(key):
+    """DRAM bytes per launch of the kernel from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            return float(json.load(f)[key])
+    except Exception:
+        return None
+
+
 def stanford_grid(sc, device):
     """75 translations (5x5x3 lattice in the 10-90 % box) x 24 unique rotations of the 4x4x4 Euler lattice."""
     from piccolo_b200 import synth
@@ -58,16 +67,18 @@ def stanford_grid(sc, device):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The sampler is
+    started before the warm-up (nvidia-smi needs ~100 ms to produce its first line); only the samples whose
+    timestamp falls inside [mark_begin, mark_end] are reported."""
+    Q = "timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -76,28 +87,37 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 - 0.02 <= t <= (self.t1 or t) + 0.04]
+        for r in inside or [r for _, r in self.rows[-3:]]:
             try:
-                sm.append(float(r[1])); smax.append(float(r[2]))
+                sm.append(float(r[2])); smax.append(float(r[3])); power.append(float(r[4]))
                 for k, nm in enumerate(names):
-                    if r[5 + k].lower().startswith("active"):
+                    if r[6 + k].lower().startswith("active"):
                         reasons.add(nm)
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm),
+                "window": "timed region" if inside else "last samples (none fell inside the timed region)"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -197,15 +217,16 @@ def run_ours(args):
     # ---- device-resident steps ------------------------------------------------------------------
     names = ["step0", "score0", "score1", "rerank1", "refine0", "refine1", "step1"]
     result = None
+    clock = ClockSampler(local_rank)
+    if rank == 0:
+        clock.start()
     for _ in range(args.warmup):
         result = pipeline.localize_query(cloud, image, grid, cfg, img=img)
         if ws > 1:
             pdist.gather_results(torch.cat([result["pose"], result["loss"].reshape(1)]))
     evs = [{n: torch.cuda.Event(enable_timing=True) for n in names} for _ in range(args.steps)]
-    clock = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        clock.start()
+    clock.mark_begin()
     l0 = _lib.launch_count()
     t_wall = time.perf_counter()
     for s in range(args.steps):
@@ -217,6 +238,7 @@ def run_ours(args):
         evs[s]["step1"].record()
     barrier()
     t_wall = time.perf_counter() - t_wall
+    clock.mark_end()
     launches = _lib.launch_count() - l0
     clocks = clock.stop() if rank == 0 else None
     step_ms = [e["step0"].elapsed_time(e["step1"]) for e in evs]
@@ -253,6 +275,7 @@ def run_ours(args):
         bwd_achieved = ALGO_BYTES_PER_EVAL * cfg.num_input * args.n_points / bwd_launch_s / 1e9
         sc_launch_s = (sum(score_ms) / len(score_ms)) * 1e-3
         sc_achieved = ALGO_BYTES_PER_EVAL * P * args.n_points / sc_launch_s / 1e9
+        default_size = (args.n_points == 1_000_000 and args.height == 1024)
         pose = result["pose"].cpu().numpy().astype(np.float64)
         Rg, Rf = synth.rot_zyx(*sc.gt_pose[3:]), synth.rot_zyx(*pose[3:])
         r_err = float(np.rad2deg(np.arccos(np.clip((np.trace(Rf.T @ Rg) - 1) / 2, -1, 1))))
@@ -262,13 +285,17 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, P, cfg),
             "sec_per_query": total_ms / args.steps * 1e-3,
             "phases_ms": {"score": sum(score_ms) / len(score_ms), "topk_hist_rerank": sum(rerank_ms) / len(rerank_ms), "refine": sum(refine_ms) / len(refine_ms)},
-            "roofline": {"kernel": "pcl_sample_kernel<fmt,BWD=1> (fused fwd+bwd+reduce+Adam+plateau+clamp, one launch per iteration)",
-                         "bound": "hbm", "achieved": bwd_achieved, "peak": peak, "unit": "GB/s", "frac": bwd_achieved / peak, "traffic": None,
-                         "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_EVAL * cfg.num_input * args.n_points,
-                         "launch_us": bwd_launch_s * 1e6, "evals_per_s": cfg.num_input * args.n_points / bwd_launch_s},
-            "roofline_score": {"kernel": "pcl_sample_kernel<fmt,BWD=0> (forward-only grid scoring)", "bound": "hbm", "achieved": sc_achieved, "peak": peak,
-                               "unit": "GB/s", "frac": sc_achieved / peak, "traffic": None, "launch_us": sc_launch_s * 1e6,
-                               "evals_per_s": P * args.n_points / sc_launch_s},
+            "roofline": None,
+            "roofline_refine": {"kernel": "pcl_sample_kernel<fmt,BWD=1> (fused fwd+bwd+reduce+Adam+plateau+clamp, one launch per iteration, B=6)",
+                                "bound": "hbm", "achieved": bwd_achieved, "peak": peak, "unit": "GB/s", "frac": bwd_achieved / peak,
+                                "traffic": ncu_traffic("C2_refine_launch_bytes") if default_size else None,
+                                "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_EVAL * cfg.num_input * args.n_points,
+                                "launch_us": bwd_launch_s * 1e6, "evals_per_s": cfg.num_input * args.n_points / bwd_launch_s},
+            "roofline_score": {"kernel": "pcl_sample_kernel<fmt,BWD=0> (forward-only grid scoring, one launch for the 1800-pose grid)", "bound": "hbm",
+                               "achieved": sc_achieved, "peak": peak, "unit": "GB/s", "frac": sc_achieved / peak,
+                               "traffic": ncu_traffic("C2_score_launch_bytes") if default_size else None,
+                               "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_EVAL * P * args.n_points,
+                               "launch_us": sc_launch_s * 1e6, "evals_per_s": P * args.n_points / sc_launch_s},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 28, "sec_per_query": e2e_ms / e2e_steps * 1e-3,
                     "steps": e2e_steps},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
@@ -280,6 +307,8 @@ def run_ours(args):
                                     "sample": f"24 of {P} grid poses forward-only ({r['score_s']:.1f} s) + 2 of {cfg.num_iter} refinement iterations B={cfg.num_input} "
                                               f"({r['refine_s']:.1f} s) of the same workload, oracle ATen-chain port, {torch.get_num_threads()} threads",
                                     "sec_per_query_extrapolated": q_evals / (r["evals"] / r["seconds"])}
+        # `roofline` = the kernel with the larger share of the step (ncu launch list: profiles/r1_launch_list_bench_C2.md)
+        line["roofline"] = dict(line["roofline_score"] if sum(score_ms) >= sum(refine_ms) else line["roofline_refine"])
         print(json.dumps(line))
     if ws > 1:
         dist.destroy_process_group()
