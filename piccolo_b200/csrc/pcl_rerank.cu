@@ -29,15 +29,17 @@ __global__ void pcl_rr_splat_kernel(const PclCloudView C, const PclPose* __restr
   const float qx = P.r00 * dx + P.r01 * dy + P.r02 * dz;
   const float qy = P.r10 * dx + P.r11 * dy + P.r12 * dz;
   const float qz = P.r20 * dx + P.r21 * dy + P.r22 * dz;
-  const float dist = sqrtf(qx * qx + qy * qy + qz * qz);
-  // cloud2idx, fp32 op for op (utils.py:44-59), then make_pano's pixel truncation (utils.py:159-165)
-  const float theta = atan2f(sqrtf(qx * qx + qy * qy), qz + 1e-6f);
-  const float phi = atan2f(qy, qx + 1e-6f) + 3.14159265358979323846f;
-  const float u = 2.0f * (1.0f - phi / 6.28318530717958647692f) - 1.0f;
+  // cloud2idx, fp32 op for op (utils.py:44-59) with the kernels' minimax atan2 (1e-7 rad: moves a point across a
+  // pixel-truncation boundary with probability ~1e-5), then make_pano's pixel truncation (utils.py:159-165).
+  // Rows first: only the middle row blocks are ever compared, points landing elsewhere stop here.
+  const float theta = pcl_atan2_pos(sqrtf(qx * qx + qy * qy), qz + 1e-6f);
   const float v = 2.0f * (theta / 3.14159265358979323846f) - 1.0f;
-  const int x = (int)(((u + 1.0f) / 2.0f) * (float)(W - 1));
   const int y = (int)(((v + 1.0f) / 2.0f) * (float)(H - 1));
   if (y + 1 < y_lo || y - 1 >= y_hi) return;
+  const float phi = pcl_atan2(qy, qx + 1e-6f) + 3.14159265358979323846f;
+  const float u = 2.0f * (1.0f - phi / 6.28318530717958647692f) - 1.0f;
+  const int x = (int)(((u + 1.0f) / 2.0f) * (float)(W - 1));
+  const float dist = sqrtf(qx * qx + qy * qy + qz * qz);
   const unsigned long long base = ((unsigned long long)(~__float_as_uint(dist)) << PCL_IDX_BITS) | ((unsigned long long)i & PCL_IDX_MASK);
   unsigned long long* img = keys + (size_t)blockIdx.y * (size_t)(y_hi - y_lo) * (size_t)W;
   const int yp = min(y + 1, H - 1), ym = max(y - 1, 0), xp = min(x + 1, W - 1), xm = max(x - 1, 0);
@@ -45,9 +47,12 @@ __global__ void pcl_rr_splat_kernel(const PclCloudView C, const PclPose* __restr
   const int ys[9] = {y, y, ym, ym, ym, yp, yp, yp, y};
   const int xs[9] = {xm, xp, xm, x, xp, xm, x, xp, x};
 #pragma unroll
-  for (int r = 0; r < 9; ++r) {
-    if (ys[r] >= y_lo && ys[r] < y_hi)
-      atomicMax(img + (size_t)(ys[r] - y_lo) * (size_t)W + (size_t)xs[r], ((unsigned long long)(r + 1) << 60) | base);
+  for (int r = 8; r >= 0; --r) {              // centre first: it wins most pixels, later (weaker) keys are filtered by the read
+    if (ys[r] >= y_lo && ys[r] < y_hi) {
+      unsigned long long* cell = img + (size_t)(ys[r] - y_lo) * (size_t)W + (size_t)xs[r];
+      const unsigned long long key = ((unsigned long long)(r + 1) << 60) | base;
+      if (__ldcg(cell) < key) atomicMax(cell, key);      // a stale read only costs a redundant atomic, never a wrong result
+    }
   }
 }
 
@@ -57,9 +62,9 @@ __device__ __forceinline__ int pcl_rr_bin(float r, float g, float b) {
   return br + 8 * bg + 64 * bb;
 }
 
-// query side, once per image: per compared block the normalised 512-bin histogram and the pixel count
+// query side, once per image: raw 512-bin histogram counts per compared block (blockIdx.y slices the rows)
 __global__ void pcl_rr_img_hist_kernel(const float* __restrict__ img, const int H, const int W, const int nsh, const int nsw,
-                                       float* __restrict__ img_hist /*[nblk][512]*/, int* __restrict__ n_gt /*[nblk]*/) {
+                                       unsigned int* __restrict__ img_hist /*[nblk][512]*/, unsigned int* __restrict__ n_gt /*[nblk]*/) {
   __shared__ unsigned int hist[512];
   __shared__ unsigned int total;
   const int blk = blockIdx.x, bh = H / nsh, bw = W / nsw;
@@ -67,21 +72,22 @@ __global__ void pcl_rr_img_hist_kernel(const float* __restrict__ img, const int 
   for (int i = threadIdx.x; i < 512; i += blockDim.x) hist[i] = 0;
   if (threadIdx.x == 0) total = 0;
   __syncthreads();
-  for (int p = threadIdx.x; p < bh * bw; p += blockDim.x) {
+  for (int p = blockIdx.y * blockDim.x + threadIdx.x; p < bh * bw; p += gridDim.y * blockDim.x) {
     const int y = h * bh + p / bw, x = w * bw + p % bw;
     const float* px = img + ((size_t)y * W + x) * 3;
     const float r = px[0], g = px[1], b = px[2];
     if (!(r * 255.0f == 0.0f && g * 255.0f == 0.0f && b * 255.0f == 0.0f)) { atomicAdd(&hist[pcl_rr_bin(r, g, b)], 1u); atomicAdd(&total, 1u); }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) img_hist[blk * 512 + i] = (float)hist[i] / (float)total;
-  if (threadIdx.x == 0) n_gt[blk] = (int)total;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) if (hist[i]) atomicAdd(&img_hist[blk * 512 + i], hist[i]);
+  if (threadIdx.x == 0 && total) atomicAdd(&n_gt[blk], total);
 }
 
 // candidate side: one CTA per (block, candidate)
 __global__ void pcl_rr_cand_hist_kernel(const PclCloudView C, const float* __restrict__ img, const unsigned long long* __restrict__ keys,
                                         const int H, const int W, const int nsh, const int nsw, const int y_lo, const int y_hi,
-                                        const float* __restrict__ img_hist, float* __restrict__ inter /*[K][nblk]*/, int* __restrict__ n_tgt) {
+                                        const unsigned int* __restrict__ img_hist, const unsigned int* __restrict__ n_gt,
+                                        float* __restrict__ inter /*[K][nblk]*/, int* __restrict__ n_tgt) {
   __shared__ unsigned int hist[512];
   __shared__ unsigned int total;
   __shared__ float red[32];
@@ -105,8 +111,8 @@ __global__ void pcl_rr_cand_hist_kernel(const PclCloudView C, const float* __res
   }
   __syncthreads();
   float s = 0.0f;
-  const float tot = (float)total;
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) s += fminf(img_hist[blk * 512 + i], (float)hist[i] / tot);
+  const float tot = (float)total, gtot = (float)n_gt[blk];      // hist / hist.sum() on both sides (color_utils.py:103)
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) s += fminf((float)img_hist[blk * 512 + i] / gtot, (float)hist[i] / tot);
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -119,24 +125,34 @@ __global__ void pcl_rr_cand_hist_kernel(const PclCloudView C, const float* __res
 }
 
 // The reference's loop, quirks included (utils.py:547-579): the split table persists across candidates, an empty
-// block writes 0 and BREAKS the inner (column) loop, NaN -> 0, mean over ALL nsh*nsw cells.
-__global__ void pcl_rr_final_kernel(const float* __restrict__ inter, const int* __restrict__ n_tgt, const int* __restrict__ n_gt,
+// block writes 0 and BREAKS the inner (column) loop (cells to its right keep the previous candidate's value),
+// NaN -> 0, mean over ALL nsh*nsw cells.  One thread per table cell walks the candidates in order; the per-
+// candidate sum over cells is a block reduction.  Launch with 64 threads.
+__global__ void pcl_rr_final_kernel(const float* __restrict__ inter, const int* __restrict__ n_tgt, const unsigned int* __restrict__ n_gt,
                                     const int K, const int nsh, const int nsw, float* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  float split[64];
-  for (int i = 0; i < nsh * nsw; ++i) split[i] = 0.0f;
-  const int nblk = (nsh - 2) * nsw;
+  __shared__ float red[2];
+  const int cell = threadIdx.x, ncell = nsh * nsw, nblk = (nsh - 2) * nsw;
+  const int h = cell / nsw, w = cell - h * nsw;
+  const bool compared = cell < ncell && h >= 1 && h < nsh - 1;
+  float cur = 0.0f;
   for (int c = 0; c < K; ++c) {
-    for (int h = 1; h < nsh - 1; ++h) {
-      for (int w = 0; w < nsw; ++w) {
-        const int blk = (h - 1) * nsw + w;
-        if (n_tgt[c * nblk + blk] == 0 || n_gt[blk] == 0) { split[h * nsw + w] = 0.0f; break; }
-        split[h * nsw + w] = inter[c * nblk + blk];
+    if (compared) {
+      // first empty column of this row for this candidate (the `break`)
+      int first_empty = nsw;
+      for (int ww = 0; ww <= w; ++ww) {
+        const int blk = (h - 1) * nsw + ww;
+        if (n_tgt[c * nblk + blk] == 0 || n_gt[blk] == 0u) { first_empty = ww; break; }
       }
+      if (w < first_empty) cur = inter[c * nblk + (h - 1) * nsw + w];
+      else if (w == first_empty) cur = 0.0f;
+      if (isnan(cur)) cur = 0.0f;
     }
-    float s = 0.0f;
-    for (int i = 0; i < nsh * nsw; ++i) { if (isnan(split[i])) split[i] = 0.0f; s += split[i]; }
-    out[c] = s / (float)(nsh * nsw);
+    float s = (cell < ncell) ? cur : 0.0f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) out[c] = (red[0] + red[1]) / (float)ncell;
+    __syncthreads();
   }
 }
 
@@ -151,17 +167,18 @@ extern "C" int pcl_hist_rerank(const pcl_cloud* c, const float* img_hw3_dev, int
   const size_t key_bytes = (size_t)k * (size_t)(y_hi - y_lo) * (size_t)w * sizeof(unsigned long long);
   const size_t off_pose = (key_bytes + 255) & ~(size_t)255;
   const size_t off_ih = off_pose + (((size_t)k * sizeof(PclPose) + 255) & ~(size_t)255);
-  const size_t off_ngt = off_ih + (size_t)nblk * 512 * sizeof(float);
+  const size_t off_ngt = off_ih + (size_t)nblk * 512 * sizeof(unsigned int);
   const size_t off_inter = off_ngt + (((size_t)nblk * sizeof(int) + 255) & ~(size_t)255);
   const size_t off_ntgt = off_inter + (((size_t)k * nblk * sizeof(float) + 255) & ~(size_t)255);
   const size_t total = off_ntgt + (size_t)k * nblk * sizeof(int);
   char* buf;
   PCL_CUDA(pcl_pool_alloc((void**)&buf, total, st));
   PCL_CUDA(cudaMemsetAsync(buf, 0, key_bytes, st));
+  PCL_CUDA(cudaMemsetAsync(buf + off_ih, 0, off_inter - off_ih, st));
   unsigned long long* keys = (unsigned long long*)buf;
   PclPose* poses = (PclPose*)(buf + off_pose);
-  float* img_hist = (float*)(buf + off_ih);
-  int* n_gt = (int*)(buf + off_ngt);
+  unsigned int* img_hist = (unsigned int*)(buf + off_ih);
+  unsigned int* n_gt = (unsigned int*)(buf + off_ngt);
   float* inter = (float*)(buf + off_inter);
   int* n_tgt = (int*)(buf + off_ntgt);
   PclCloudView C = {c->x, c->y, c->z, c->r, c->g, c->b, (long long)c->n};
@@ -169,11 +186,11 @@ extern "C" int pcl_hist_rerank(const pcl_cloud* c, const float* img_hw3_dev, int
   PCL_LAUNCH_CHECK();
   pcl_rr_splat_kernel<<<dim3((unsigned int)((c->n + 255) / 256), k), 256, 0, st>>>(C, poses, h, w, y_lo, y_hi, keys);
   PCL_LAUNCH_CHECK();
-  pcl_rr_img_hist_kernel<<<nblk, 512, 0, st>>>(img_hw3_dev, h, w, num_split_h, num_split_w, img_hist, n_gt);
+  pcl_rr_img_hist_kernel<<<dim3(nblk, 32), 256, 0, st>>>(img_hw3_dev, h, w, num_split_h, num_split_w, img_hist, n_gt);
   PCL_LAUNCH_CHECK();
-  pcl_rr_cand_hist_kernel<<<dim3(nblk, k), 512, 0, st>>>(C, img_hw3_dev, keys, h, w, num_split_h, num_split_w, y_lo, y_hi, img_hist, inter, n_tgt);
+  pcl_rr_cand_hist_kernel<<<dim3(nblk, k), 512, 0, st>>>(C, img_hw3_dev, keys, h, w, num_split_h, num_split_w, y_lo, y_hi, img_hist, n_gt, inter, n_tgt);
   PCL_LAUNCH_CHECK();
-  pcl_rr_final_kernel<<<1, 32, 0, st>>>(inter, n_tgt, n_gt, k, num_split_h, num_split_w, hist_intersect_k_dev);
+  pcl_rr_final_kernel<<<1, 64, 0, st>>>(inter, n_tgt, n_gt, k, num_split_h, num_split_w, hist_intersect_k_dev);
   PCL_LAUNCH_CHECK();
   pcl_pool_free(buf, st);
   return PCL_OK;
