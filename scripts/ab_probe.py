@@ -22,6 +22,6 @@ for rep in range(3):
 print(os.environ.get("PCL_LIB", "default"), os.environ.get("PCL_NT_BWD", ""), " | ".join(out))
 '''
 for lib in sys.argv[1:]:
-    for nt in (("256", "320") if "prev" not in lib else ("256",)):
+    for nt in ("256",):
         env = dict(os.environ, PCL_LIB=os.path.abspath(lib), PCL_NT_BWD=nt)
         subprocess.run([sys.executable, "-c", code], env=env)
