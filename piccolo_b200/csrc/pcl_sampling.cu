@@ -301,6 +301,9 @@ static PclLaunchPlan pcl_plan(const pcl_cloud* c, int64_t P, bool bwd) {
   // pose block: as many poses per CTA as possible (point loads amortise over the block) while leaving
   // enough CTAs to fill the machine
   int PB = (int)(P < PCL_MAX_POSE_BLOCK ? P : PCL_MAX_POSE_BLOCK);
+  // small refinement batches: two pose blocks (twice the rows per CTA, half the row-count imbalance) measured
+  // 8 % faster than one block of all candidates (B=6: 47 vs 51 us per iteration)
+  if (bwd && P >= 4 && P <= 16) PB = (int)((P + 1) / 2);
   const int pb_env = pcl_env_int(bwd ? "PCL_PB_BWD" : "PCL_PB_FWD", 0);
   if (pb_env > 0 && pb_env <= PCL_MAX_POSE_BLOCK) PB = (int)(pb_env < P ? pb_env : P);
   pl.PB = PB;

@@ -45,8 +45,9 @@ def test_c1_sequential_query_localises_and_matches_oracle():
     cfg = Cfg(6, 0.1, 100, 5, 0.8, 0.05)
     res = omniloc_all(img, xyz, rgb, tt, rr, cfg)
     one = omniloc(img, xyz, rgb, tt, rr, 1, cfg, None)
-    # the batched sequential-semantics run IS the per-candidate loop (independent trajectories)
-    assert torch.equal(res[1][0], one[0]) and torch.equal(res[1][2], one[2])
+    # the batched sequential-semantics run IS the per-candidate loop (independent trajectories); the launch geometry
+    # (and with it the fp32 summation grouping) depends on the batch size, so equality is up to rounding noise
+    assert (res[1][0] - one[0]).abs().max() < 2e-3 and abs(float(res[1][2]) - float(one[2])) < 0.02 * float(one[2])
     best = int(np.argmin([float(r[2]) for r in res]))
     t = res[best][0].numpy().reshape(3)
     assert np.linalg.norm(t - sc.gt_pose[:3]) < 0.05                      # localises (reference threshold: 0.2 m)
