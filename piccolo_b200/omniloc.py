@@ -73,19 +73,16 @@ class BatchSamplingLoss(nn.Module):
 
 
 def _rotation_from_angles(yaw, pitch, roll, device):
-    """R = Rz·Ry·Rx rebuilt from the final angles exactly like omniloc.py:71-87."""
-    tensor_0 = torch.zeros(1, device=device)
-    tensor_1 = torch.ones(1, device=device)
-    RX = torch.stack([torch.stack([tensor_1, tensor_0, tensor_0]),
-                      torch.stack([tensor_0, cos(roll), -sin(roll)]),
-                      torch.stack([tensor_0, sin(roll), cos(roll)])]).reshape(3, 3)
-    RY = torch.stack([torch.stack([cos(pitch), tensor_0, sin(pitch)]),
-                      torch.stack([tensor_0, tensor_1, tensor_0]),
-                      torch.stack([-sin(pitch), tensor_0, cos(pitch)])]).reshape(3, 3)
-    RZ = torch.stack([torch.stack([cos(yaw), -sin(yaw), tensor_0]),
-                      torch.stack([sin(yaw), cos(yaw), tensor_0]),
-                      torch.stack([tensor_0, tensor_0, tensor_1])]).reshape(3, 3)
-    return torch.mm(torch.mm(RZ, RY), RX)
+    """R = Rz(yaw)·Ry(pitch)·Rx(roll) of the final angles (what omniloc.py:71-87 rebuilds), in closed form:
+        [ cy·cp   cy·sp·sr − sy·cr   cy·sp·cr + sy·sr ]
+        [ sy·cp   sy·sp·sr + cy·cr   sy·sp·cr − cy·sr ]
+        [ −sp     cp·sr              cp·cr            ]"""
+    y, p, r = [a.reshape(()).to(device=device, dtype=torch.float32) for a in (yaw, pitch, roll)]
+    cy, sy, cp, sp, cr, sr = cos(y), sin(y), cos(p), sin(p), cos(r), sin(r)
+    rows = [[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+            [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+            [-sp, cp * sr, cp * cr]]
+    return torch.stack([torch.stack(row) for row in rows])
 
 
 def _cfg_train(cfg):
