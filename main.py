@@ -13,11 +13,11 @@ from piccolo_b200.parse_utils import apply_override, parse_ini, parse_override, 
 
 
 def main():
-    parser = argparse.ArgumentParser()
-    parser.add_argument("--config", help="Config file to use for running experiments", default=None, type=str)
-    parser.add_argument("--log", help="Log directory for logging accuracy", default="./log", type=str)
-    parser.add_argument("--override", default=None, help="Arguments for overriding config")
-    args = parser.parse_args()
+    cli = argparse.ArgumentParser(description="PICCOLO sampling-loss localisation on the B200 CUDA path")
+    cli.add_argument("--config", type=str, default=None, help=".ini file (configs/stanford.ini, configs/stanford_parallel.ini, configs/omniscenes.ini)")
+    cli.add_argument("--log", type=str, default="./log", help="output directory: config.ini, *_results.csv, TensorBoard events, results/*.png")
+    cli.add_argument("--override", default=None, help='config overrides, "key=value,key2=value2"')
+    args = cli.parse_args()
     cfg = parse_ini(args.config)
     os.makedirs(args.log, exist_ok=True)
     from torch.utils.tensorboard import SummaryWriter
