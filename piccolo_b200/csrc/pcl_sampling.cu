@@ -2,14 +2,17 @@
 //
 // One kernel template does all three.  Work decomposition (B200: 148 SMs):
 //   grid.y  = pose blocks (<= PCL_MAX_POSE_BLOCK poses, their R|t live in shared memory)
-//   grid.x  = point chunks; a CTA walks tiles of 256*K points (tile, tile+grid.x, ...)
-//   thread  = K points held in registers (SoA, coalesced 32-bit loads; lane i <-> point i, so with a
+//   grid.x  = balanced contiguous ranges of rows (row = 256 consecutive points); the whole grid is a whole number
+//             of resident waves (3 CTAs/SM forward, 2 forward+backward), so there is no tail wave
+//   thread  = 4 or 5 points held in registers (SoA, coalesced 32-bit loads; lane i <-> point i, so with a
 //             Morton-ordered cloud the 32 lanes of a warp gather texels from one small image patch)
-//   per (tile, pose): K evaluations per thread, warp-shuffle reduction, lane 0 accumulates into the
-//             warp's private shared-memory row (no atomics on the hot loop)
-//   per CTA: one row of partial sums per pose to global memory; the LAST CTA of a pose block
-//             (ticket counter) reduces the rows in fixed order (deterministic) in fp64 and finishes:
+//   per (row group, pose): 4-5 evaluations per thread, halving-butterfly warp reduction, a few lanes add into the
+//             warp's private fp64 shared-memory row (no atomics on the hot loop)
+//   per CTA: one fp64 partial record per pose to global memory; the LAST CTA of a pose block (ticket counter)
+//             reduces the records in a fixed two-level order (deterministic) and finishes:
 //             loss (score) | loss + 6-DoF gradient | loss + gradient + Adam + plateau + clamp (refine)
+//   refinement iterations are launched with programmatic dependent launch: the next iteration's prologue overlaps
+//             the previous iteration's tail.
 //
 // Replaces: utils.py:484-499 (grid scoring), omniloc.py:171-202 / :311-356 (+ autograd backward),
 //           omniloc.py:44-58 / :249-269 (optimiser step, scheduler step, clamp).
