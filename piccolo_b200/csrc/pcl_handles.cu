@@ -269,6 +269,15 @@ extern "C" int pcl_image_create(const float* img, int h, int w, int format, void
     im->bytes = (size_t)(h + 1) * (w + 1) * 32; im->view.tex_scale = 1.0f / 255.0f;
     PCL_CUDA(pcl_pool_alloc(&im->data, im->bytes, st));
     grid.y = h + 1;
+    if (format == PCL_IMAGE_AUTO) {      // compact companion table for small refinement batches (see pcl_common.cuh)
+      pcl_image_set_geometry(im->view_small, h, w, w + 1);
+      im->view_small.fmt = PCL_IMAGE_U8Q; im->view_small.tex_scale = 1.0f / 255.0f;
+      PCL_CUDA(pcl_pool_alloc(&im->data_small, (size_t)(h + 1) * (w + 1) * 16, st));
+      pcl_build_u8q_kernel<<<grid, block, 0, st>>>(img, h, w, (uint4*)im->data_small);
+      PCL_LAUNCH_CHECK();
+      im->view_small.data = im->data_small;
+      im->has_small = 1;
+    }
     pcl_build_f16d_kernel<<<grid, block, 0, st>>>(img, h, w, (uint4*)im->data);
   } else if (fmt == PCL_IMAGE_U8P) {
     im->bytes = (size_t)(h + 2) * (w + 2) * 4; im->view.tex_scale = 1.0f / 255.0f;
@@ -322,6 +331,7 @@ extern "C" void pcl_image_destroy(pcl_image* im) {
   } else {
     pcl_pool_free(im->data, im->owner);
   }
+  if (im->has_small) pcl_pool_free(im->data_small, im->owner);
   free(im);
 }
 

@@ -347,13 +347,15 @@ static int pcl_launch(const PclLaunchPlan& pl, const pcl_cloud* c, const pcl_ima
                       double* partial, unsigned int* counters, const PclFinalize& fin, cudaStream_t st, bool pdl = false) {
   PclCloudView C = {c->x, c->y, c->z, c->r, c->g, c->b, (long long)c->n};
   cudaError_t e;
-  switch (im->view.fmt) {
-    case PCL_FMT_U8Q: e = pcl_launch_fmt<PCL_FMT_U8Q, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st, pdl); break;
-    case PCL_FMT_U8P: e = pcl_launch_fmt<PCL_FMT_U8P, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st, pdl); break;
-    case PCL_FMT_F32: e = pcl_launch_fmt<PCL_FMT_F32, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st, pdl); break;
-    case PCL_FMT_TEX: e = pcl_launch_fmt<PCL_FMT_TEX, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st, pdl); break;
-    case PCL_FMT_F16D: e = pcl_launch_fmt<PCL_FMT_F16D, BWD>(pl, C, im->view, poses, P, partial, counters, fin, st, pdl); break;
-    default: pcl_set_error("unknown image format %d", im->view.fmt); return PCL_ERR_INVALID;
+  // small forward+backward batches (refinement) read the compact companion table when the image has one
+  const PclImage& view = (BWD && P <= 16 && im->has_small && pcl_env_int("PCL_SMALL_TABLE", 1)) ? im->view_small : im->view;
+  switch (view.fmt) {
+    case PCL_FMT_U8Q: e = pcl_launch_fmt<PCL_FMT_U8Q, BWD>(pl, C, view, poses, P, partial, counters, fin, st, pdl); break;
+    case PCL_FMT_U8P: e = pcl_launch_fmt<PCL_FMT_U8P, BWD>(pl, C, view, poses, P, partial, counters, fin, st, pdl); break;
+    case PCL_FMT_F32: e = pcl_launch_fmt<PCL_FMT_F32, BWD>(pl, C, view, poses, P, partial, counters, fin, st, pdl); break;
+    case PCL_FMT_TEX: e = pcl_launch_fmt<PCL_FMT_TEX, BWD>(pl, C, view, poses, P, partial, counters, fin, st, pdl); break;
+    case PCL_FMT_F16D: e = pcl_launch_fmt<PCL_FMT_F16D, BWD>(pl, C, view, poses, P, partial, counters, fin, st, pdl); break;
+    default: pcl_set_error("unknown image format %d", view.fmt); return PCL_ERR_INVALID;
   }
   g_pcl_launches.fetch_add(1);
   PCL_CUDA(e);

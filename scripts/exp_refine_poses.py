@@ -6,7 +6,7 @@ import bench
 dev = torch.device("cuda:0")
 sc = synth.make_scene(1_000_000, 1024, 2048, seed=3)
 xyz, rgb, img = [torch.from_numpy(a).to(dev) for a in (sc.xyz, sc.rgb, sc.img)]
-cloud, image = engine.Cloud(xyz, rgb), engine.Image(img)
+cloud, image = engine.Cloud(xyz, rgb), engine.Image(img, os.environ.get("PROBE_FMT", "auto"))
 grid = bench.stanford_grid(sc, dev)
 out = pipeline.localize_query(cloud, image, grid, pipeline.STANFORD_PARALLEL, img=img)
 starts = grid.index_select(0, out["start_index"])
