@@ -317,3 +317,18 @@ def test_histogram_rerank_matches_reference(golden):
     np.testing.assert_array_equal(rr[0].cpu().numpy(), g["top6_rot"][0])
     again = engine.hist_rerank(engine.get_cloud(xyz_t, rgb_t), img_t, poses, 4, 4).cpu().numpy()
     np.testing.assert_array_equal(again, scores)             # atomicMax of unique keys: deterministic
+
+
+def test_large_refinement_batch_matches_oracle(golden):
+    """B = 40 candidates (two pose blocks of the large-batch path, F16D table) for 3 iterations vs the oracle."""
+    from piccolo_b200 import engine
+    g = golden("refine_small")
+    rgb, img = synth.rgb_from_u8(g["rgb8"]), synth.img_from_u8(g["img8"])
+    rng = np.random.default_rng(4)
+    starts = np.stack([g["gt_pose"] + np.concatenate([rng.normal(0, 0.3, 3), rng.normal(0, 0.2, 3)]) for _ in range(40)]).astype(np.float32)
+    cloud, image = engine.Cloud(cu(g["xyz"]), cu(rgb)), engine.Image(cu(img))
+    for bs in (False, True):
+        out = engine.Refiner(40, 0.1, 0.8, 5, bs).reset(cu(starts)).run(cloud, image, 3).read()
+        o = orc.refine_np(g["xyz"], rgb, img, starts, lr=0.1, num_iter=3, patience=5, factor=0.8, q=0.05, batch_semantics=bs, dtype=np.float32)
+        np.testing.assert_allclose(out["pose"].cpu().numpy(), o["pose"], atol=3e-4)
+        np.testing.assert_allclose(out["loss"].cpu().numpy(), o["loss"], rtol=1e-3)
