@@ -73,11 +73,20 @@ __global__ void pcl_gather_kernel(const float* __restrict__ xyz, const float* __
   r[i] = rgb[3 * s]; g[i] = rgb[3 * s + 1]; b[i] = rgb[3 * s + 2];
 }
 
+static int pcl_cloud_build(pcl_cloud* c, const float* xyz, const float* rgb, int64_t n, double q, int order, cudaStream_t st);
+
 extern "C" int pcl_cloud_create(const float* xyz, const float* rgb, int64_t n, double q, int order, void* stream, pcl_cloud** out) {
   if (!xyz || !rgb || !out || n <= 0 || n > 0x7fffff00ll) { pcl_set_error("bad cloud arguments (n=%lld)", (long long)n); return PCL_ERR_INVALID; }
   if (!(q >= 0.0 && q <= 1.0)) { pcl_set_error("quantile %g outside [0,1]", q); return PCL_ERR_INVALID; }
-  cudaStream_t st = (cudaStream_t)stream;
   pcl_cloud* c = (pcl_cloud*)calloc(1, sizeof(pcl_cloud));
+  if (!c) { pcl_set_error("out of host memory"); return PCL_ERR_INVALID; }
+  const int rc = pcl_cloud_build(c, xyz, rgb, n, q, order, (cudaStream_t)stream);
+  if (rc != PCL_OK) { pcl_cloud_destroy(c); return rc; }      // nothing leaks on a failed build
+  *out = c;
+  return PCL_OK;
+}
+
+static int pcl_cloud_build(pcl_cloud* c, const float* xyz, const float* rgb, int64_t n, double q, int order, cudaStream_t st) {
   c->n = n;
   c->n_pad = (n + PCL_TILE_ALIGN - 1) / PCL_TILE_ALIGN * PCL_TILE_ALIGN;
   c->order = order;
@@ -138,7 +147,6 @@ extern "C" int pcl_cloud_create(const float* xyz, const float* rgb, int64_t n, d
     pcl_pool_free(tmp, st); pcl_pool_free(sorted, st);
   }
   pcl_pool_free(scratch, st);
-  *out = c;
   return PCL_OK;
 }
 
@@ -158,7 +166,7 @@ extern "C" int pcl_cloud_bounds(const pcl_cloud* c, float* lo_hi) {
 
 extern "C" void pcl_cloud_destroy(pcl_cloud* c) {
   if (!c) return;
-  pcl_pool_free(c->block, c->owner);
+  if (c->block) pcl_pool_free(c->block, c->owner);
   free(c);
 }
 
@@ -228,9 +236,20 @@ __global__ void pcl_build_f32_kernel(const float* __restrict__ img, int H, int W
   tab[(size_t)ye * (W + 2) + xe] = v;
 }
 
+static int pcl_image_build(pcl_image* im, const float* img, int h, int w, int format, cudaStream_t st);
+
 extern "C" int pcl_image_create(const float* img, int h, int w, int format, void* stream, pcl_image** out) {
   if (!img || !out || h < 2 || w < 2 || h > 32768 || w > 65536) { pcl_set_error("bad image arguments (%d x %d)", h, w); return PCL_ERR_INVALID; }
-  cudaStream_t st = (cudaStream_t)stream;
+  pcl_image* im = (pcl_image*)calloc(1, sizeof(pcl_image));
+  if (!im) { pcl_set_error("out of host memory"); return PCL_ERR_INVALID; }
+  im->owner = (cudaStream_t)stream;
+  const int rc = pcl_image_build(im, img, h, w, format, (cudaStream_t)stream);
+  if (rc != PCL_OK) { pcl_image_destroy(im); return rc; }      // nothing leaks on a failed build
+  *out = im;
+  return PCL_OK;
+}
+
+static int pcl_image_build(pcl_image* im, const float* img, int h, int w, int format, cudaStream_t st) {
   int fmt = format;
   if (fmt == PCL_IMAGE_AUTO || fmt == PCL_IMAGE_U8Q || fmt == PCL_IMAGE_U8P || fmt == PCL_IMAGE_TEX || fmt == PCL_IMAGE_F16D) {
     int* flag; int host_flag = 0;
@@ -255,8 +274,6 @@ extern "C" int pcl_image_create(const float* img, int h, int w, int format, void
     pcl_set_error("unknown image format %d", format);
     return PCL_ERR_INVALID;
   }
-  pcl_image* im = (pcl_image*)calloc(1, sizeof(pcl_image));
-  im->owner = st;
   pcl_image_set_geometry(im->view, h, w, (fmt == PCL_IMAGE_U8Q || fmt == PCL_IMAGE_F16D) ? w + 1 : w + 2);
   im->view.fmt = fmt;
   dim3 block(128), grid((w + 2 + 127) / 128, 1);
@@ -317,7 +334,6 @@ extern "C" int pcl_image_create(const float* img, int h, int w, int format, void
   if (fmt != PCL_IMAGE_TEX) PCL_LAUNCH_CHECK();
   PCL_CUDA(cudaStreamSynchronize(st));
   im->view.data = im->data;
-  *out = im;
   return PCL_OK;
 }
 
@@ -326,9 +342,9 @@ extern "C" int pcl_image_format(const pcl_image* im) { return im ? im->view.fmt 
 extern "C" void pcl_image_destroy(pcl_image* im) {
   if (!im) return;
   if (im->view.fmt == PCL_FMT_TEX) {
-    cudaDestroyTextureObject((cudaTextureObject_t)im->view.tex);
-    cudaFreeArray((cudaArray_t)im->data);
-  } else {
+    if (im->view.tex) cudaDestroyTextureObject((cudaTextureObject_t)im->view.tex);
+    if (im->data) cudaFreeArray((cudaArray_t)im->data);
+  } else if (im->data) {
     pcl_pool_free(im->data, im->owner);
   }
   if (im->has_small) pcl_pool_free(im->data_small, im->owner);

@@ -164,7 +164,6 @@ def make_pano(xyz: torch.Tensor, rgb: torch.Tensor, resolution=(200, 400), retur
     """Painter's-algorithm render of camera-frame points to an equirectangular image (utils.py:134-205), used for
     the result PNGs.  Deterministic version of the reference's nine `index_put_` calls: nearest point wins, the
     centre write beats the 3x3 dilation writes."""
-    from .omniloc import _rotation_from_angles  # noqa: F401  (keeps import graph identical on CPU-only machines)
     import numpy as np
     H, W = resolution
     with torch.no_grad():
