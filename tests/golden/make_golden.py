@@ -128,6 +128,37 @@ def main():
                         pano20=pano.numpy())
     print("rerank_small: best pose", tr6[0].numpy(), "gt", sch.gt_pose[:3])
 
+    # ---------------- fixture 2c: candidate grids (generate_rot_points / generate_trans_points) ------------
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_localize_cfg", os.path.join(REF, "parse_utils.py"))
+    ref_parse = importlib.util.module_from_spec(spec); spec.loader.exec_module(ref_parse)
+    grids = {}
+    scg = synth.make_scene(50000, 32, 64, seed=2)
+    xg = torch.from_numpy(scg.xyz)
+    for name in ("stanford", "omniscenes"):
+        cfgg = ref_parse.parse_ini(os.path.join(REF, "configs", name + ".ini"))
+        import localize as ref_localize
+        init = ref_localize.get_init_dict(cfgg)
+        grids[name + "_rot"] = ref_utils.generate_rot_points(init).numpy()
+        grids[name + "_trans"] = ref_utils.generate_trans_points(xg, init).numpy()
+    np.savez_compressed(os.path.join(HERE, "grids_small.npz"), xyz=scg.xyz, **grids)
+    print("grids:", {k: v.shape for k, v in grids.items()})
+
+    # ---------------- fixture 2d: one full C1 query through the reference (make_input + omniloc) ----------
+    if os.environ.get("GOLDEN_C1", "1") == "1":
+        sc1 = synth.make_scene(200000, 512, 1024, seed=3)
+        x1, c1, i1 = torch.from_numpy(sc1.xyz), torch.from_numpy(sc1.rgb), torch.from_numpy(sc1.img)
+        cfg1 = ref_parse.parse_ini(os.path.join(REF, "configs", "stanford.ini"))
+        init1 = ref_localize.get_init_dict(cfg1)
+        np.random.seed(2); torch.manual_seed(2)
+        in_t, in_r = ref_utils.make_input(i1, x1, c1, cfg1.num_input, init1, cfg1.criterion, cfg1.num_intermediate)
+        res = [ref_omniloc.omniloc(i1, x1, c1, in_t, in_r, k, cfg1, None) for k in range(cfg1.num_input)]
+        best = int(np.argmin([float(r[2]) for r in res]))
+        np.savez_compressed(os.path.join(HERE, "query_c1.npz"), gt_pose=sc1.gt_pose, input_trans=in_t.numpy(), input_rot=in_r.numpy(),
+                            final_t=np.stack([r[0].detach().numpy().reshape(3) for r in res]), final_R=np.stack([r[1].detach().numpy() for r in res]),
+                            final_loss=np.array([float(r[2]) for r in res], dtype=np.float32), best=best)
+        print("query_c1: best", best, "t", res[best][0].detach().numpy().reshape(3), "gt", sc1.gt_pose[:3], "losses", [round(float(r[2]), 4) for r in res])
+
     # ---------------- fixture 3: refinement trajectories (omniloc / omniloc_batch) -------------
     def run_refine(scn, starts, num_iter, tag, factor, early_iter):
         """omniloc per candidate + omniloc_batch in fp32 (the parity target), the same after `early_iter`
