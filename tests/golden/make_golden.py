@@ -152,7 +152,10 @@ def main():
         init1 = ref_localize.get_init_dict(cfg1)
         np.random.seed(2); torch.manual_seed(2)
         in_t, in_r = ref_utils.make_input(i1, x1, c1, cfg1.num_input, init1, cfg1.criterion, cfg1.num_intermediate)
+        # omniloc optimises VIEWS of input_trans / input_rot in place (omniloc.py:15-19): keep the start poses
+        start_t, start_r = in_t.clone(), in_r.clone()
         res = [ref_omniloc.omniloc(i1, x1, c1, in_t, in_r, k, cfg1, None) for k in range(cfg1.num_input)]
+        in_t, in_r = start_t, start_r
         best = int(np.argmin([float(r[2]) for r in res]))
         np.savez_compressed(os.path.join(HERE, "query_c1.npz"), gt_pose=sc1.gt_pose, input_trans=in_t.numpy(), input_rot=in_r.numpy(),
                             final_t=np.stack([r[0].detach().numpy().reshape(3) for r in res]), final_R=np.stack([r[1].detach().numpy() for r in res]),
