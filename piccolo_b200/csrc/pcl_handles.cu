@@ -36,29 +36,29 @@ __global__ void pcl_bbox_kernel(const float* __restrict__ xyz, long long n, unsi
   }
 }
 
-__device__ __forceinline__ unsigned long long pcl_spread21(unsigned long long v) {   // 21 bits -> every third bit
-  v &= 0x1fffffull;
-  v = (v | (v << 32)) & 0x1f00000000ffffull;
-  v = (v | (v << 16)) & 0x1f0000ff0000ffull;
-  v = (v | (v << 8)) & 0x100f00f00f00f00full;
-  v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
-  v = (v | (v << 2)) & 0x1249249249249249ull;
+__device__ __forceinline__ unsigned int pcl_spread10(unsigned int v) {   // 10 bits -> every third bit
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
   return v;
 }
 
+// 30-bit Morton code (10 bits per axis: 1024^3 cells — finer than the point spacing needed for lane locality);
+// 32-bit keys halve the radix-sort passes of the one-off packing step
 __global__ void pcl_morton_kernel(const float* __restrict__ xyz, long long n, const unsigned int* mm,
-                                  unsigned long long* keys, unsigned int* idx) {
+                                  unsigned int* keys, unsigned int* idx) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  unsigned long long code = 0;
+  unsigned int code = 0;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const float lo = pcl_float_unorder(mm[k]), hi = pcl_float_unorder(mm[3 + k]);
     const float ext = fmaxf(hi - lo, 1e-20f);
     float t = (xyz[3 * i + k] - lo) / ext;
     t = fminf(fmaxf(t, 0.0f), 1.0f);
-    const unsigned long long qv = (unsigned long long)(t * 2097151.0f);
-    code |= pcl_spread21(qv) << k;
+    code |= pcl_spread10((unsigned int)(t * 1023.0f)) << k;
   }
   keys[i] = code;
   idx[i] = (unsigned int)i;
@@ -102,17 +102,17 @@ static int pcl_cloud_build(pcl_cloud* c, const float* xyz, const float* rgb, int
   unsigned int* perm = nullptr;
   void* scratch = nullptr;
   if (order == PCL_CLOUD_MORTON) {
-    unsigned int* mm; unsigned long long *k_in, *k_out; unsigned int *v_in, *v_out;
+    unsigned int* mm; unsigned int *k_in, *k_out; unsigned int *v_in, *v_out;
     size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
-                                    (unsigned int*)nullptr, (unsigned int*)nullptr, (int)n, 0, 63, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (unsigned int*)nullptr, (unsigned int*)nullptr,
+                                    (unsigned int*)nullptr, (unsigned int*)nullptr, (int)n, 0, 30, st);
     const size_t nb = (size_t)n;
-    const size_t total = 64 + nb * 8 * 2 + nb * 4 * 2 + tmp_bytes + 256;
+    const size_t total = 64 + nb * 4 * 2 + nb * 4 * 2 + tmp_bytes + 256;
     PCL_CUDA(pcl_pool_alloc(&scratch, total, st));
     char* pch = (char*)scratch;
     mm = (unsigned int*)pch; pch += 64;
-    k_in = (unsigned long long*)pch; pch += nb * 8;
-    k_out = (unsigned long long*)pch; pch += nb * 8;
+    k_in = (unsigned int*)pch; pch += nb * 4;
+    k_out = (unsigned int*)pch; pch += nb * 4;
     v_in = (unsigned int*)pch; pch += nb * 4;
     v_out = (unsigned int*)pch; pch += nb * 4;
     pch = (char*)(((uintptr_t)pch + 255) & ~(uintptr_t)255);
@@ -122,7 +122,7 @@ static int pcl_cloud_build(pcl_cloud* c, const float* xyz, const float* rgb, int
     PCL_LAUNCH_CHECK();
     pcl_morton_kernel<<<blocks, threads, 0, st>>>(xyz, n, mm, k_in, v_in);
     PCL_LAUNCH_CHECK();
-    PCL_CUDA(cub::DeviceRadixSort::SortPairs(pch, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, 63, st));
+    PCL_CUDA(cub::DeviceRadixSort::SortPairs(pch, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, 30, st));
     perm = v_out;
   }
   pcl_gather_kernel<<<blocks, threads, 0, st>>>(xyz, rgb, perm, n, c->x, c->y, c->z, c->r, c->g, c->b);
