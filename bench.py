@@ -175,7 +175,7 @@ def workload_config(args, n_grid, cfg):
     return {"workload": "C2: stanford_parallel.ini settings, synthetic textured room", "n_points": args.n_points,
             "panorama": f"{args.height}x{2*args.height}", "grid_poses": int(n_grid), "num_input": cfg.num_input, "num_iter": cfg.num_iter,
             "refine_semantics": "omniloc_batch", "queries_per_gpu_per_step": 1,
-            "l2": "flushed between steps (256 MiB write); inputs (58 MB) are smaller than L2"}
+            "l2": "flushed between steps (256 MiB write): packed cloud 24 MB + texel tables 100 MB would otherwise stay partly L2-resident"}
 
 
 # --------------------------------------------------------------------------------------------------
