@@ -60,10 +60,11 @@ def ncu_traffic(key):
 def stanford_grid(sc, device):
     """75 translations (5x5x3 lattice in the 10-90 % box) x 24 unique rotations of the 4x4x4 Euler lattice."""
     from piccolo_b200 import synth
-    from piccolo_b200.utils import generate_rot_points, grid_poses
+    from piccolo_b200.pipeline import StartGrid
+    from piccolo_b200.utils import generate_rot_points
     rot = generate_rot_points({"yaw_only": False, "num_yaw": 4, "num_pitch": 4, "num_roll": 4})
     trans = torch.from_numpy(np.ascontiguousarray(synth.pose_grid(sc.room, (5, 5, 3), 1)[:, :3]))
-    return grid_poses(trans, rot).to(device)
+    return StartGrid(trans, rot).to(device)
 
 
 class ClockSampler:
@@ -151,7 +152,7 @@ def run_reference(args):
     from piccolo_b200 import pipeline, synth
     cfg = pipeline.STANFORD_PARALLEL
     sc = synth.make_scene(args.n_points, args.height, 2 * args.height, seed=SCENE_SEED)
-    grid = stanford_grid(sc, "cpu")
+    grid = stanford_grid(sc, "cpu").poses()
     n_score, n_iter = 12, 1
     for _ in range(args.warmup):
         cpu_port_sample(sc, grid, cfg, 2, 1)
@@ -201,8 +202,8 @@ def run_ours(args):
         gt = synth.random_gt_pose(sc.room, seed=SCENE_SEED + rank)
         sc = synth.Scene(sc.xyz, sc.rgb8, synth.render_panorama(gt, args.height, 2 * args.height, sc.room), gt, sc.room)
     grid = stanford_grid(sc, device)
-    P = grid.shape[0]
-    xyz_h, rgb_h, img_h, grid_h = [torch.from_numpy(a).pin_memory() for a in (sc.xyz, sc.rgb, sc.img)] + [grid.cpu().pin_memory()]
+    P = len(grid)
+    xyz_h, rgb_h, img_h, grid_h = [torch.from_numpy(a).pin_memory() for a in (sc.xyz, sc.rgb, sc.img)] + [grid.to("cpu").pin_memory()]
     xyz, rgb, img = xyz_h.to(device), rgb_h.to(device), img_h.to(device)
     cloud = engine.Cloud(xyz, rgb, cfg.out_of_room_quantile)
     image = engine.Image(img)
@@ -267,7 +268,7 @@ def run_ours(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
     e2e_value = ws * q_evals * e2e_steps / (e2e_ms * 1e-3)
-    h2d = int(xyz_h.numel() * 4 + rgb_h.numel() * 4 + img_h.numel() * 4 + grid_h.numel() * 4)
+    h2d = int(xyz_h.numel() * 4 + rgb_h.numel() * 4 + img_h.numel() * 4 + grid_h.trans.numel() * 4 + grid_h.rot.numel() * 4)
 
     if rank == 0:
         peak, peak_kind = measured_hbm_peak()
@@ -291,18 +292,22 @@ def run_ours(args):
                                 "traffic": ncu_traffic("C2_refine_launch_bytes") if default_size else None,
                                 "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_EVAL * cfg.num_input * args.n_points,
                                 "launch_us": bwd_launch_s * 1e6, "evals_per_s": cfg.num_input * args.n_points / bwd_launch_s},
-            "roofline_score": {"kernel": "pcl_sample_kernel<fmt,BWD=0> (forward-only grid scoring, one launch for the 1800-pose grid)", "bound": "hbm",
+            "roofline_score": {"kernel": "pcl_grid_score_kernel<fmt> (structured-grid forward-only scoring, one launch for the 75x24 start grid; rotations related "
+                                         "by an in-plane turn share transform/elevation/azimuth per point)", "bound": "hbm",
                                "achieved": sc_achieved, "peak": peak, "unit": "GB/s", "frac": sc_achieved / peak,
                                "traffic": ncu_traffic("C2_score_launch_bytes") if default_size else None,
                                "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_EVAL * P * args.n_points,
-                               "launch_us": sc_launch_s * 1e6, "evals_per_s": P * args.n_points / sc_launch_s},
+                               "launch_us": sc_launch_s * 1e6, "evals_per_s": P * args.n_points / sc_launch_s,
+                               "note": "frac > 1 is possible: SURVEY 8d's figure charges one 24-byte point read per pose*point evaluation, while a loaded "
+                                       "point is reused for all poses of a CTA (actual DRAM traffic: `traffic`); the kernel's real co-roofs are L1/TEX "
+                                       "gather wavefronts (83 %) and instruction issue (75 %), profiles/r1_ncu_full_grid_score_C2.md"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 28, "sec_per_query": e2e_ms / e2e_steps * 1e-3,
                     "steps": e2e_steps},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
             "result": {"t_error_m": float(np.linalg.norm(pose[:3] - sc.gt_pose[:3])), "r_error_deg": r_err, "loss": float(result["loss"].item())},
         }
         if ws == 1 and not args.no_cpu_baseline:
-            r = cpu_port_sample(sc, grid.cpu(), cfg, 24, 2)
+            r = cpu_port_sample(sc, grid.poses().cpu(), cfg, 24, 2)
             line["cpu_baseline"] = {"value": r["evals"] / r["seconds"], "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": f"24 of {P} grid poses forward-only ({r['score_s']:.1f} s) + 2 of {cfg.num_iter} refinement iterations B={cfg.num_input} "
                                               f"({r['refine_s']:.1f} s) of the same workload, oracle ATen-chain port, {torch.get_num_threads()} threads",

@@ -9,6 +9,7 @@
  *   pcl_image_create   the per-query upload `img.to(device)`                    (localize.py:169-170, :212-213)
  *   pcl_score          the T×R forward-only loop of `trim_input_loss`           (utils.py:484-499)
  *                      and `sampling_loss`                                      (omniloc.py:105-157)
+ *   pcl_score_grid     the same loop, given as translations x rotations        (utils.py:484-499)
  *   pcl_topk           `loss_table.flatten().argsort()[:num_input]`             (utils.py:501-502)
  *   pcl_loss_fwd_bwd   `SamplingLoss.forward` + autograd backward               (omniloc.py:171-202)
  *                      `BatchSamplingLoss.forward` + backward                   (omniloc.py:311-356)
@@ -89,6 +90,14 @@ void pcl_image_destroy(pcl_image* im);
 /* loss_p_dev[p] = Σ m·e / Σ m (NaN when no point survives the zero mask); count_p_dev (nullable) = Σ m */
 int pcl_score(const pcl_cloud* c, const pcl_image* im, const float* poses_p6_dev, int64_t p,
               float* loss_p_dev, float* count_p_dev, void* stream);
+
+/* The same table for a structured start grid: every translation i < T against every rotation j < R, output index
+ * i*R + j — the double loop of trim_input_loss (utils.py:484-499) over generate_trans_points x generate_rot_points.
+ * Rotations of the list that differ by an in-plane turn about the camera z axis (all yaw-only lists; the Euler
+ * lattice's 24 rotations = 6 groups of 4) share the rigid transform, elevation and one azimuth atan2 per point.
+ * trans_t3_dev: (T,3), rot_r3_dev: (R,3) (yaw, pitch, roll); loss/count: (T*R). */
+int pcl_score_grid(const pcl_cloud* c, const pcl_image* im, const float* trans_t3_dev, int64_t t,
+                   const float* rot_r3_dev, int r, float* loss_tr_dev, float* count_tr_dev, void* stream);
 
 /* indices of the k smallest losses, ascending, ties -> lower index, NaN last */
 int pcl_topk(const float* loss_p_dev, int64_t p, int k, int64_t* idx_k_dev, void* stream);

@@ -169,7 +169,8 @@ __device__ __forceinline__ void pcl_process_rows(const PclCloudView& C, const Pc
 template <int FMT, bool BWD>
 __global__ void __launch_bounds__(PCL_THREADS, BWD ? 2 : 3)
 pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, const int P, const int PB,
-                  const long long n_rows, double* __restrict__ partial, unsigned int* __restrict__ counters, const PclFinalize fin) {
+                  const long long n_rows, double* __restrict__ partial, unsigned int* __restrict__ counters, const PclFinalize fin,
+                  const int swap) {
   constexpr int NS = BWD ? PCL_NSUM : 2;
   __shared__ __align__(16) PclPose s_pose[PCL_MAX_POSE_BLOCK];
   __shared__ double s_acc[PCL_WARPS][PCL_MAX_POSE_BLOCK][NS];   // fp64: row-to-row accumulation adds no fp32 error
@@ -177,7 +178,10 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
   __shared__ int s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int p0 = blockIdx.y * PB;
+  // block order: pose blocks fastest (swap) keeps the co-resident CTAs on few row ranges
+  const unsigned int bp = swap ? blockIdx.x : blockIdx.y, br = swap ? blockIdx.y : blockIdx.x;
+  const unsigned int n_ranges = swap ? gridDim.y : gridDim.x;
+  const int p0 = bp * PB;
   const int np = min(PB, P - p0);
 
   for (int i = tid; i < PCL_WARPS * PCL_MAX_POSE_BLOCK * NS; i += PCL_THREADS) (&s_acc[0][0][0])[i] = 0.0;
@@ -192,8 +196,8 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
   __syncthreads();
 
   // balanced contiguous row range of this CTA (sizes differ by at most one row of 256 points)
-  const long long r_begin = n_rows * (long long)blockIdx.x / (long long)gridDim.x;
-  const long long r_end = n_rows * (long long)(blockIdx.x + 1) / (long long)gridDim.x;
+  const long long r_begin = n_rows * (long long)br / (long long)n_ranges;
+  const long long r_end = n_rows * (long long)(br + 1) / (long long)n_ranges;
   long long r = r_begin;
   const long long r_full = min(r_end, C.n / PCL_THREADS);      // rows below r_full have 256 real points
   {
@@ -214,15 +218,15 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
     double t = 0.0;
 #pragma unroll
     for (int w = 0; w < PCL_WARPS; ++w) t += s_acc[w][p][s];
-    partial[((size_t)blockIdx.x * (size_t)P + (size_t)(p0 + p)) * NS + s] = t;
+    partial[((size_t)br * (size_t)P + (size_t)(p0 + p)) * NS + s] = t;
   }
 
   // last-block-done
   __threadfence();
   __syncthreads();
   if (tid == 0) {
-    const unsigned int ticket = atomicAdd(&counters[blockIdx.y], 1u);
-    s_last = (ticket == gridDim.x - 1);
+    const unsigned int ticket = atomicAdd(&counters[bp], 1u);
+    s_last = (ticket == n_ranges - 1);
   }
   __syncthreads();
   if (!s_last) return;
@@ -240,7 +244,7 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
       const double2* src = reinterpret_cast<const double2*>(partial + (size_t)p0 * NS) + item;
       const size_t stride = (size_t)P * (NS / 2);
 #pragma unroll 16
-      for (unsigned int bx = g; bx < gridDim.x; bx += G) {
+      for (unsigned int bx = g; bx < n_ranges; bx += G) {
         const double2 v = __ldcg(src + (size_t)bx * stride);
         t.x += v.x; t.y += v.y;
       }
@@ -271,7 +275,7 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
       }
     }
   }
-  if (tid == 0) counters[blockIdx.y] = 0u;     // self-resetting: the next launch needs no memset
+  if (tid == 0) counters[bp] = 0u;     // self-resetting: the next launch needs no memset
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -331,7 +335,8 @@ static cudaError_t pcl_launch_fmt(const PclLaunchPlan& pl, const PclCloudView& C
                                   double* partial, unsigned int* counters, const PclFinalize& fin, cudaStream_t st, bool pdl) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(pl.gx, pl.gy);
+  const int swap = (!BWD && pl.gy > 1 && pl.gx <= 65535) ? pcl_env_int("PCL_SWAP", 0) : 0;
+  cfg.gridDim = swap ? dim3(pl.gy, pl.gx) : dim3(pl.gx, pl.gy);
   cfg.blockDim = dim3(PCL_THREADS);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -339,7 +344,7 @@ static cudaError_t pcl_launch_fmt(const PclLaunchPlan& pl, const PclCloudView& C
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, pcl_sample_kernel<FMT, BWD>, C, I, poses, P, pl.PB, pl.n_rows, partial, counters, fin);
+  return cudaLaunchKernelEx(&cfg, pcl_sample_kernel<FMT, BWD>, C, I, poses, P, pl.PB, pl.n_rows, partial, counters, fin, swap);
 }
 
 template <bool BWD>

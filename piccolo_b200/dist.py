@@ -40,13 +40,15 @@ def _all_gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
     return torch.cat(parts, dim=0)
 
 
-def score_sharded(score_fn: Callable[[torch.Tensor], torch.Tensor], poses: torch.Tensor) -> torch.Tensor:
+def score_sharded(score_fn: Callable[[torch.Tensor], torch.Tensor], poses: torch.Tensor, width: int = 1) -> torch.Tensor:
     """Every rank scores its contiguous slice of the flattened pose grid (index i*R+j) and all ranks end up
-    with the full loss vector, so the deterministic top-K (ties -> lower index) is identical everywhere."""
+    with the full loss vector, so the deterministic top-K (ties -> lower index) is identical everywhere.
+    score_fn maps n units to n*width losses: poses (n,6) with width 1, or the translations (n,3) of a structured
+    grid with width R (whole rows of the loss table per rank).  Returns the flat (len(poses)*width,) vector."""
     rank, ws = world()
     lo, hi = shard_bounds(poses.shape[0], rank, ws)
-    local = score_fn(poses[lo:hi]) if hi > lo else poses.new_zeros((0,))
-    return _all_gather_rows(local.reshape(-1, 1), poses.shape[0]).reshape(-1)
+    local = score_fn(poses[lo:hi]).reshape(hi - lo, width) if hi > lo else poses.new_zeros((0, width))
+    return _all_gather_rows(local, poses.shape[0]).reshape(-1)
 
 
 def refine_sharded(refine_fn: Callable[[torch.Tensor], torch.Tensor], starts: torch.Tensor) -> torch.Tensor:

@@ -124,6 +124,27 @@ def score(cloud: Cloud, image: Image, poses: torch.Tensor):
     return loss, count
 
 
+def score_grid(cloud: Cloud, image: Image, trans: torch.Tensor, rot: torch.Tensor):
+    """Forward-only loss of the T x R start grid (translation i, rotation j) -> flat index i*R+j, the loop of
+    `trim_input_loss` (utils.py:484-499).  Rotations related by an in-plane turn about the camera z axis share most
+    of the per-point work (pcl_grid.cu).  Returns (loss (T*R,), count (T*R,)) on the device."""
+    lib = _lib.load()
+    _require_cuda(trans, "trans")
+    _require_cuda(rot, "rot")
+    t, r = _f32c(trans), _f32c(rot)
+    if t.dim() != 2 or t.shape[1] != 3 or r.dim() != 2 or r.shape[1] != 3:
+        raise _lib.PiccoloError(f"trans must be (T,3) and rot (R,3) = (yaw,pitch,roll); got {tuple(t.shape)}, {tuple(r.shape)}")
+    P = t.shape[0] * r.shape[0]
+    loss = torch.empty(P, dtype=torch.float32, device=t.device)
+    count = torch.empty(P, dtype=torch.float32, device=t.device)
+    if P == 0:
+        return loss, count
+    with torch.cuda.device(t.device):
+        _lib.check(lib.pcl_score_grid(cloud._h, image._h, t.data_ptr(), t.shape[0], r.data_ptr(), r.shape[0], loss.data_ptr(), count.data_ptr(),
+                                      _stream(t.device)))
+    return loss, count
+
+
 def loss_fwd_bwd(cloud: Cloud, image: Image, poses: torch.Tensor):
     """Loss and analytic 6-DoF gradient of B poses in one launch.  Returns (loss (B,), count (B,), grad (B,6))."""
     lib = _lib.load()

@@ -16,6 +16,41 @@ STANFORD = TrainCfg(6, 50, 0.1, 100, 5, 0.8, 0.05, False)
 STANFORD_PARALLEL = STANFORD._replace(parallel=True)
 
 
+class StartGrid:
+    """The start grid as the reference builds it: T translations x R rotations, pose index i*R+j
+    (utils.py:484-485).  Scored by the structured-grid kernel; `localize_query*` also accept a plain (P,6) tensor."""
+
+    def __init__(self, trans: torch.Tensor, rot: torch.Tensor):
+        self.trans = trans.to(torch.float32).contiguous()
+        self.rot = rot.to(torch.float32).contiguous()
+
+    def __len__(self):
+        return self.trans.shape[0] * self.rot.shape[0]
+
+    def to(self, device, non_blocking=False):
+        return StartGrid(self.trans.to(device, non_blocking=non_blocking), self.rot.to(device, non_blocking=non_blocking))
+
+    def pin_memory(self):
+        return StartGrid(self.trans.pin_memory(), self.rot.pin_memory())
+
+    def rows(self, lo: int, hi: int) -> "StartGrid":
+        """translations [lo, hi) x all rotations = flat indices [lo*R, hi*R)"""
+        return StartGrid(self.trans[lo:hi], self.rot)
+
+    def index_select(self, dim: int, idx: torch.Tensor) -> torch.Tensor:
+        R = self.rot.shape[0]
+        return torch.cat([self.trans.index_select(0, idx // R), self.rot.index_select(0, idx % R)], dim=1)
+
+    def poses(self) -> torch.Tensor:
+        return grid_poses(self.trans, self.rot)
+
+
+def _score(cloud, image, grid):
+    if isinstance(grid, StartGrid):
+        return engine.score_grid(cloud, image, grid.trans, grid.rot)[0]
+    return engine.score(cloud, image, grid)[0]
+
+
 def query_evals(n_points: int, n_grid: int, cfg) -> int:
     """pose·point evaluations of one query: forward-only grid scoring + num_iter fused fwd+bwd iterations."""
     return n_points * (n_grid + cfg.num_iter * cfg.num_input)
@@ -23,7 +58,7 @@ def query_evals(n_points: int, n_grid: int, cfg) -> int:
 
 def localize_query(cloud: engine.Cloud, image: engine.Image, grid: torch.Tensor, cfg, timers=None, img: torch.Tensor = None,
                    num_split=(4, 4)):
-    """grid (P,6) start poses on the device.  Returns dict(pose (6,), loss, index, candidates (B,6), losses (B,)).
+    """grid: (P,6) start poses on the device, or a StartGrid (translations x rotations).  Returns dict(pose (6,), loss, index, candidates (B,6), losses (B,)).
 
     Candidate selection as `make_input` (utils.py:624-627): the `num_intermediate` grid poses with the smallest
     sampling loss, re-ranked by colour-histogram intersection down to `num_input`.  The re-rank needs the raw
@@ -35,7 +70,7 @@ def localize_query(cloud: engine.Cloud, image: engine.Image, grid: torch.Tensor,
             ev[name].record()
 
     mark("score0")
-    loss, _ = engine.score(cloud, image, grid)
+    loss = _score(cloud, image, grid)
     mark("score1")
     if img is not None:
         idx = engine.topk(loss, cfg.num_intermediate)
@@ -57,13 +92,13 @@ def localize_query(cloud: engine.Cloud, image: engine.Image, grid: torch.Tensor,
             "start_index": idx}
 
 
-def localize_query_host(xyz_h: torch.Tensor, rgb_h: torch.Tensor, img_h: torch.Tensor, grid_h: torch.Tensor, cfg, device):
+def localize_query_host(xyz_h: torch.Tensor, rgb_h: torch.Tensor, img_h: torch.Tensor, grid_h, cfg, device):
     """End-to-end call with HOST (pinned) buffers: upload, pack, score, refine, and read the answer back.
     Returns (pose (6,) cpu, loss cpu float)."""
     xyz = xyz_h.to(device, non_blocking=True)
     rgb = rgb_h.to(device, non_blocking=True)
     img = img_h.to(device, non_blocking=True)
-    grid = grid_h.to(device, non_blocking=True)
+    grid = grid_h.to(device, non_blocking=True)          # (P,6) tensor or StartGrid
     cloud = engine.Cloud(xyz, rgb, cfg.out_of_room_quantile)
     image = engine.Image(img)
     out = localize_query(cloud, image, grid, cfg, img=img)
@@ -78,7 +113,11 @@ def localize_query_sharded(cloud: engine.Cloud, image: engine.Image, grid: torch
     (loss, pose) rows are all-gathered before the arg-min.  Cloud and panorama are replicated on every GPU.
     Returns the same dict as `localize_query` on every rank."""
     from . import dist as pdist
-    loss = pdist.score_sharded(lambda p: engine.score(cloud, image, p)[0], grid)
+    if isinstance(grid, StartGrid):      # shard the translations: rank slices are whole rows of the loss table
+        R = grid.rot.shape[0]
+        loss = pdist.score_sharded(lambda tr: engine.score_grid(cloud, image, tr, grid.rot)[0], grid.trans, width=R)
+    else:
+        loss = pdist.score_sharded(lambda p: engine.score(cloud, image, p)[0], grid)
     if img is not None:
         idx = engine.topk(loss, cfg.num_intermediate)
         mid = grid.index_select(0, idx)

@@ -16,10 +16,10 @@ def grid_poses(trans: torch.Tensor, rot: torch.Tensor) -> torch.Tensor:
 
 
 def score_grid(img, xyz, rgb, trans, rot, q: float = 0.05) -> torch.Tensor:
-    """loss_table (T,R) of utils.py:481-499 from one kernel launch."""
+    """loss_table (T,R) of utils.py:481-499 from one kernel launch (structured-grid scoring, pcl_grid.cu)."""
     cloud = engine.get_cloud(xyz, rgb, q)
     image = engine.get_image(img)
-    loss, _ = engine.score(cloud, image, grid_poses(trans, rot))
+    loss, _ = engine.score_grid(cloud, image, trans, rot)
     return loss.reshape(trans.shape[0], rot.shape[0])
 
 

@@ -23,7 +23,7 @@ xyz_np, rgb8 = synth.sample_room_points(N, room, seed=2)
 xyz, rgb = torch.from_numpy(xyz_np).to(dev), torch.from_numpy(synth.rgb_from_u8(rgb8)).to(dev)
 cloud = engine.Cloud(xyz, rgb)
 init = {"yaw_only": True, "num_yaw": 8, "xy_only": True, "num_trans": 150, "z_prior": 1.5, "trans_init_mode": "quantile", "dataset": "OmniScenes"}
-grid = grid_poses(generate_trans_points(xyz, init, device=dev), generate_rot_points(init, device=dev))
+grid = pipeline.StartGrid(generate_trans_points(xyz, init, device=dev), generate_rot_points(init, device=dev))
 cfg = pipeline.STANFORD_PARALLEL
 lo, hi = shard_bounds(Q, rank, ws)
 # queries of this rank: seeded GT poses (yaw-only, z at the prior), perturbed panoramas (gamma, white balance, re-textured patches)
@@ -61,8 +61,8 @@ stat = torch.tensor([float(ok), float(len(errs))], device=dev)
 if ws > 1:
     dist.all_reduce(stat)
 if rank == 0:
-    evals = Q * pipeline.query_evals(N, grid.shape[0], cfg)
-    print(f"C4: ranks={ws} N={N} queries={Q} grid={grid.shape[0]} poses: {dt:.3f} s total, {dt/Q*1e3:.1f} ms/query wall ({dt/max(1,hi-lo)*1e3:.1f} ms per query per GPU), "
+    evals = Q * pipeline.query_evals(N, len(grid), cfg)
+    print(f"C4: ranks={ws} N={N} queries={Q} grid={len(grid)} poses: {dt:.3f} s total, {dt/Q*1e3:.1f} ms/query wall ({dt/max(1,hi-lo)*1e3:.1f} ms per query per GPU), "
           f"{evals/dt/1e9:.1f} G pp/s aggregate; localised {int(stat[0])}/{int(stat[1])} (t<0.1 m, r<5 deg)")
 if ws > 1:
     dist.destroy_process_group()

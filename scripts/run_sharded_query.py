@@ -20,6 +20,8 @@ grid_np = synth.pose_grid(room, (side, side, 1), 16)
 gt = sc.gt_pose.copy()
 near = grid_np[np.argmin(np.linalg.norm(grid_np[:, :3] - gt[:3], axis=1) + 10 * np.abs(((grid_np[:, 3] - gt[3] + np.pi) % (2 * np.pi)) - np.pi))]
 xyz, rgb, img, grid = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (sc.xyz, sc.rgb, sc.img, grid_np)]
+if os.environ.get("PCL_PLAIN_GRID", "0") != "1":            # translations x yaws: structured-grid scoring
+    grid = pipeline.StartGrid(grid[::16, :3], grid[:16, 3:])
 cloud, image = engine.Cloud(xyz, rgb), engine.Image(img)
 cfg = pipeline.STANFORD_PARALLEL
 out = pipeline.localize_query_sharded(cloud, image, grid, cfg, img=img)       # warm-up
@@ -39,8 +41,8 @@ if rank == 0:
     t1 = time.perf_counter(); single = pipeline.localize_query(cloud, image, grid, cfg, img=img); torch.cuda.synchronize(); dt1 = time.perf_counter() - t1
     same_starts = bool(torch.equal(torch.sort(single["start_index"]).values, torch.sort(out["start_index"]).values))
     dpos = float(np.linalg.norm(pose[:3] - single["pose"].cpu().numpy()[:3]))
-    evals = pipeline.query_evals(N, grid.shape[0], cfg)
-    print(f"ranks={ws} N={N} pano={H}x{2*H} grid={grid.shape[0]}: sharded {dt*1e3:.1f} ms/query ({evals/dt/1e9:.1f} G pp/s) vs single-GPU {dt1*1e3:.1f} ms; "
+    evals = pipeline.query_evals(N, len(grid), cfg)
+    print(f"ranks={ws} N={N} pano={H}x{2*H} grid={len(grid)}: sharded {dt*1e3:.1f} ms/query ({evals/dt/1e9:.1f} G pp/s) vs single-GPU {dt1*1e3:.1f} ms; "
           f"same candidate set={same_starts}; |t_sharded - t_single|={dpos*1e3:.2f} mm; t_err vs GT {np.linalg.norm(pose[:3]-gt[:3])*1e3:.1f} mm; format={image.format}")
     assert same_starts and dpos < 0.01
 if ws > 1:

@@ -29,6 +29,36 @@ static void run(const PclImage& I, const float* xyz, const float* rgb, long n, c
   }
 }
 
+// structured grid: losses of (translation t, base rotation ypr) for members with azimuth offsets delta[]
+template <int FMT>
+static void run_grid(const PclImage& I, const float* xyz, const float* rgb, long n, const float* base_pose6, const float* delta, int nm,
+                     float* loss, float* cnt) {
+  PclPose pose; pcl_pose_from_params(base_pose6, pose);
+  for (int m = 0; m < nm; ++m) {
+    double se = 0, sm = 0;
+    for (long i = 0; i < n; ++i) {
+      PclGridBase b; pcl_grid_base(pose, I, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], b);
+      float e = 0.f, c = 0.f;
+      pcl_grid_member<FMT>(I, b, delta[m], rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], true, e, c);
+      se += e; sm += c;
+    }
+    loss[m] = (float)(se / sm); cnt[m] = (float)sm;
+  }
+}
+
+extern "C" int emul_grid(const float* xyz, const float* rgb, long n, const float* img, int H, int W, const float* base_pose6,
+                         const float* delta, int nm, float* loss, float* cnt) {
+  PclImage I; std::memset(&I, 0, sizeof(I));
+  pcl_image_set_geometry(I, H, W, W + 2);
+  I.fmt = PCL_FMT_F32; I.tex_scale = 1.0f;
+  std::vector<float> f32((size_t)(H + 2) * (W + 2) * 4, 0.0f);
+  for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x)
+    for (int c = 0; c < 3; ++c) f32[((size_t)(y + 1) * (W + 2) + (x + 1)) * 4 + c] = img[((size_t)y * W + x) * 3 + c];
+  I.data = f32.data();
+  run_grid<PCL_FMT_F32>(I, xyz, rgb, n, base_pose6, delta, nm, loss, cnt);
+  return 0;
+}
+
 extern "C" int emul_loss_grad(const float* xyz, const float* rgb, long n, const float* img, int H, int W, int fmt,
                               const float* poses, int P, int bwd, float* loss, float* cnt, float* grad) {
   PclImage I; std::memset(&I, 0, sizeof(I));

@@ -28,6 +28,11 @@ def _worker(rank, ws, port, q):
             return orc.sampling_loss_torch(xyz, rgb, img, p)[0]
 
         full = pd.score_sharded(score_fn, poses)
+        # the same table sharded by translation (structured grid: whole rows of R losses per unit)
+        trans, rot = poses[::5, :3].contiguous(), poses[:5, 3:].contiguous()
+        assert torch.equal(torch.cat([trans.repeat_interleave(5, 0), rot.repeat(len(trans), 1)], 1), poses)
+        by_rows = pd.score_sharded(lambda tr: score_fn(torch.cat([tr.repeat_interleave(5, 0), rot.repeat(len(tr), 1)], 1)), trans, width=5)
+        assert torch.equal(by_rows, full)
         idx = torch.from_numpy(orc.topk_ascending(full.numpy(), 5))
         starts = poses[idx]
 

@@ -51,3 +51,23 @@ def test_emulated_black_image_is_nan(emul, golden):
     rgb, img = synth.rgb_from_u8(g["rgb8"]), synth.img_from_u8(g["img8"])
     loss, cnt, grad = emul(g["xyz"], rgb, np.zeros_like(img), g["poses"][:2], "u8q")
     assert np.isnan(loss).all() and (cnt == 0).all()
+
+
+def test_emulated_structured_grid_matches_reference_losses(golden):
+    """Shared elevation / shifted azimuth evaluation of rotations related by an in-plane rotation (pcl_grid_base +
+    pcl_grid_member) against the reference's per-pose losses: yaw-only members of the golden scoring grid."""
+    g = golden("score_small")
+    small = golden("loss_small")
+    rgb, img = synth.rgb_from_u8(small["rgb8"]), synth.img_from_u8(small["img8"])
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", SRC, "-o", SO])
+    lib = ctypes.CDLL(SO)
+    fp = ctypes.POINTER(ctypes.c_float)
+    xyz = np.ascontiguousarray(small["xyz"], dtype=np.float32)
+    R = len(g["rot"])                                   # 8 yaws, pitch = roll = 0: one group
+    delta = ((g["rot"][:, 0] - g["rot"][0, 0] + np.pi) % (2 * np.pi) - np.pi).astype(np.float32)
+    for ti in range(len(g["trans"])):
+        base = np.concatenate([g["trans"][ti], g["rot"][0]]).astype(np.float32)
+        loss, cnt = np.zeros(R, np.float32), np.zeros(R, np.float32)
+        lib.emul_grid(xyz.ctypes.data_as(fp), rgb.ctypes.data_as(fp), ctypes.c_long(len(xyz)), img.ctypes.data_as(fp), img.shape[0], img.shape[1],
+                      base.ctypes.data_as(fp), delta.ctypes.data_as(fp), R, loss.ctypes.data_as(fp), cnt.ctypes.data_as(fp))
+        np.testing.assert_allclose(loss, g["loss_table"][ti * R:(ti + 1) * R], rtol=2e-5)

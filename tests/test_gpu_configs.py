@@ -65,6 +65,9 @@ def test_c2_batched_query_properties():
     a = pipeline.localize_query(cloud, image, grid, pipeline.STANFORD_PARALLEL)
     b = pipeline.localize_query(cloud, image, grid, pipeline.STANFORD_PARALLEL)
     assert torch.equal(a["candidates"], b["candidates"]) and torch.equal(a["losses"], b["losses"])   # bit-reproducible
+    # structured-grid scoring (translations x rotations) selects the same starts as per-pose scoring of the (P,6) list
+    plain = pipeline.localize_query(cloud, image, grid.poses(), pipeline.STANFORD_PARALLEL)
+    assert torch.equal(plain["start_index"], a["start_index"]) and torch.equal(plain["candidates"], a["candidates"])
     pose = a["pose"].cpu().numpy()
     assert np.linalg.norm(pose[:3] - sc.gt_pose[:3]) < 0.02 and rot_err_deg(pose, sc.gt_pose) < 0.5
     # loss/gradient of the found pose agree with the fp64 oracle at full size
@@ -97,6 +100,13 @@ def test_c3_shapes_sharded_scoring_identical_topk():
     assert torch.equal(torch.cat(again), torch.cat(parts))             # each slice is bit-reproducible
     assert int(full.argmin()) == 7 and int(engine.topk(full, 1)[0]) == 7
     assert (cnt > 0).all() and torch.isfinite(full).all()
+    # structured-grid scoring of the same table (256 translations x 16 yaws = one rotation group), texture path
+    plain = cu(synth.pose_grid(sc.room, (16, 16, 1), 16))
+    sg, sg_cnt = engine.score_grid(cloud, image, plain[::16, :3].contiguous(), plain[:16, 3:].contiguous())
+    keep = torch.ones(4096, dtype=torch.bool, device=sg.device); keep[7] = False          # slot 7 holds the GT pose above
+    np.testing.assert_allclose(sg[keep].cpu().numpy(), full[keep].cpu().numpy(), rtol=2e-5)
+    assert (sg_cnt[keep] - cnt[keep]).abs().max() <= 3
+    assert torch.equal(engine.topk(sg[keep], 50), engine.topk(full[keep], 50))
     # additivity over a split of the cloud (Σ m·e and Σ m add up) at full size
     half = 5_000_000
     sub = grid[:64]

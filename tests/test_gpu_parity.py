@@ -135,6 +135,66 @@ def test_grid_scoring_and_topk_match_trim_input_loss(small, golden):
     np.testing.assert_array_equal(rr.cpu().numpy(), g["all_rot"])
 
 
+def _rot_lists():
+    from piccolo_b200 import utils as pu
+    rng = np.random.default_rng(11)
+    lattice = pu.generate_rot_points({"yaw_only": False, "num_yaw": 4, "num_pitch": 4, "num_roll": 4}).numpy()
+    yaw16 = pu.generate_rot_points({"yaw_only": True, "num_yaw": 16}).numpy()
+    tilted = yaw16[:5].copy(); tilted[:, 1] = 0.3; tilted[:, 2] = -0.2      # yaw varies under a fixed pitch/roll: still one group (Rz is leftmost)
+    rolled = yaw16[:5].copy(); rolled[:, 1] = 0.3; rolled[:, 2] = yaw16[:5, 0]   # roll varies under a pitch: 5 groups of one
+    loose = rng.uniform(-np.pi, np.pi, (7, 3)).astype(np.float32)           # no structure: 7 groups of one
+    wide = rng.uniform(-np.pi, np.pi, (40, 3)).astype(np.float32)           # R > 32: generic fallback inside the ABI
+    return {"lattice24": lattice, "yaw16": yaw16, "tilted5": tilted, "rolled5": rolled, "loose7": loose, "wide40": wide, "single": yaw16[3:4]}
+
+
+@pytest.mark.parametrize("fmt", ["auto", "u8q", "tex", "f32"])
+@pytest.mark.parametrize("name", ["lattice24", "yaw16", "tilted5", "rolled5", "loose7", "wide40", "single"])
+def test_structured_grid_scoring_matches_per_pose_scoring(small, name, fmt):
+    """pcl_score_grid (shared transform / elevation / azimuth within groups of rotations related by an in-plane
+    turn) against pcl_score on the expanded pose list, and against the fp64 oracle for a subset."""
+    from piccolo_b200 import engine, utils as pu
+    rot = _rot_lists()[name]
+    rng = np.random.default_rng(5)
+    lo, hi = small["xyz"].min(0), small["xyz"].max(0)
+    trans = (lo + (hi - lo) * rng.uniform(0.2, 0.8, (7, 3))).astype(np.float32)          # 7: ragged translation blocks
+    cloud = engine.Cloud(cu(small["xyz"]), cu(small["rgb"]), 0.05)
+    image = engine.Image(cu(small["img"]), fmt)
+    loss, cnt = engine.score_grid(cloud, image, cu(trans), cu(rot))
+    poses = pu.grid_poses(cu(trans), cu(rot))
+    ref, ref_cnt = engine.score(cloud, image, poses)
+    assert loss.shape == (len(trans) * len(rot),)
+    # The loss is discontinuous where a sample crosses the panorama seam (phi = +-pi) or the edge between black and
+    # non-black texels (zero mask): a point within ~1e-7 rad of such an edge may fall on either side in any fp32
+    # evaluation (this 4 k-point cloud has one 2.6e-8 px from the seam for one of these poses).  One such flip moves
+    # the mean by up to ~0.5/M, so: >= 95 % of the table within 2e-5, everything within one flip.
+    assert np.abs(cnt.cpu().numpy() - ref_cnt.cpu().numpy()).max() <= 3
+    got, per_pose = loss.cpu().numpy(), ref.cpu().numpy()
+    flip = 0.5 / float(ref_cnt.min())
+    rel = np.abs(got - per_pose) / per_pose
+    assert (rel < 2e-5).mean() >= 0.95 and (np.abs(got - per_pose) <= 2e-5 * per_pose + flip).all(), rel.max()
+    sub = rng.choice(len(poses), 6, replace=False)
+    want = np.array([orc.loss_and_grad_np(small["xyz"], small["rgb"], small["img"], pp, dtype=np.float64, want_grad=False)[0] for pp in poses.cpu().numpy()[sub]])
+    assert (np.abs(got[sub] - want) <= LOSS_RTOL * want + flip).all() and (np.abs(got[sub] - want) <= LOSS_RTOL * want).sum() >= 5
+    # identical ranking of the table
+    k = min(10, len(poses))
+    assert torch.equal(engine.topk(loss, k), engine.topk(ref, k))
+
+
+def test_structured_grid_errors_and_empty(small):
+    from piccolo_b200 import engine, _lib
+    cloud = engine.Cloud(cu(small["xyz"]), cu(small["rgb"]), 0.05)
+    image = engine.Image(cu(small["img"]))
+    loss, cnt = engine.score_grid(cloud, image, torch.zeros(0, 3, device=dev()), torch.zeros(4, 3, device=dev()))
+    assert loss.numel() == 0 and cnt.numel() == 0
+    with pytest.raises(_lib.PiccoloError):
+        engine.score_grid(cloud, image, torch.zeros(3, 3), torch.zeros(4, 3, device=dev()))          # CPU tensor: no CPU path
+    with pytest.raises(_lib.PiccoloError):
+        engine.score_grid(cloud, image, torch.zeros(3, 6, device=dev()), torch.zeros(4, 3, device=dev()))
+    far = torch.full((2, 3), 1e4, device=dev())                                                    # every sample valid or NaN, never a crash
+    loss, _ = engine.score_grid(cloud, image, far, torch.zeros(3, 3, device=dev()))
+    assert loss.shape == (6,)
+
+
 def test_topk_ties_nan_and_sizes():
     from piccolo_b200 import engine
     loss = np.array([0.5, np.nan, 0.2, 0.2, 0.9, 0.1, -0.0, 0.0], dtype=np.float32)
