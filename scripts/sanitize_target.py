@@ -14,6 +14,10 @@ for order in (0, 1):
     for fmt in ("auto", "f16d", "u8q", "u8p", "tex", "f32"):
         image = engine.Image(img, fmt)
         loss, cnt = engine.score(cloud, image, poses)
+        from piccolo_b200.utils import generate_rot_points
+        for rot in (generate_rot_points({"yaw_only": True, "num_yaw": 8}), generate_rot_points({"yaw_only": False, "num_yaw": 4, "num_pitch": 4, "num_roll": 4}),
+                    poses[:40, 3:].cpu()):                              # one group | 6 groups of 4 | R > 32: expanded + generic kernel
+            gl, gc = engine.score_grid(cloud, image, poses[:7, :3].contiguous(), rot.to(dev))
         l2, c2, g = engine.loss_fwd_bwd(cloud, image, poses[:40])
         l3, c3, g3 = engine.loss_fwd_bwd(cloud, image, poses[:6])
         out = engine.Refiner(6, 0.1, 0.8, 5, True).reset(poses[:6]).run(cloud, image, 4).read()
