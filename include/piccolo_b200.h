@@ -49,7 +49,7 @@ typedef enum pcl_status {
 } pcl_status;
 
 /* texel formats of a pcl_image */
-#define PCL_IMAGE_AUTO 0   /* image exactly k/255: F16D while the table fits L2 (<= 96 MB), else TEX; otherwise F32 */
+#define PCL_IMAGE_AUTO 0   /* image exactly k/255: F16D up to 2048x4096 (+ a compact U8Q/U8P companion for small gradient batches), U8Q beyond; otherwise F32 */
 #define PCL_IMAGE_U8Q 1    /* 16-byte footprint entries {nw,ne,sw,se} RGBA8: one 128-bit load per sample */
 #define PCL_IMAGE_F32 2    /* fp32 RGBA texels: arbitrary float images */
 #define PCL_IMAGE_U8P 3    /* plain RGBA8 texels (4 B/texel): smallest table, four 32-bit loads */

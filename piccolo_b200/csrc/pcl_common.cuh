@@ -52,7 +52,7 @@ struct pcl_image {
   void* data;
   size_t bytes;
   PclImage view;                // view.data == data
-  // Optional compact second table (U8Q, 16 B per footprint) used by small refinement batches: their poses move
+  // Optional compact second table (U8Q, 16 B per footprint; U8P, 4 B per texel, for panoramas above 1024x2048) used by small refinement batches: their poses move
   // every iteration, and the 32 B/footprint F16D table (67 MB at 1024x2048) does not stay L2-resident beside the
   // cloud under that access pattern (measured 55-57 vs 49 us per iteration), while it wins for scoring.
   void* data_small;

@@ -265,10 +265,12 @@ static int pcl_image_build(pcl_image* im, const float* img, int h, int w, int fo
       if (fmt != PCL_IMAGE_AUTO) { pcl_set_error("image is not exactly uint8/255: a u8 texel table would change the result"); return PCL_ERR_FORMAT; }
       fmt = PCL_IMAGE_F32;
     } else if (fmt == PCL_IMAGE_AUTO) {
-      // fastest table that stays L2-resident next to the cloud (126 MB L2): fp16 basis entries (32 B per
-      // footprint) up to 96 MB, else the 4 B/texel texture path
-      const size_t fbytes = (size_t)(h + 1) * (w + 1) * 32;
-      fmt = (fbytes <= (size_t)96 << 20) ? PCL_IMAGE_F16D : PCL_IMAGE_TEX;
+      // Measured on B200 (profiles/r1_texel_format_sizes.md): the 32-byte fp16 basis table is the fastest scoring
+      // format up to 2048x4096 (268 MB: it no longer fits the 126 MB L2, but dense clouds share sectors between
+      // lanes and the kernels' block order keeps the live slice resident); beyond that the 16-byte quad table wins,
+      // and the 4 B/texel texture only remains for panoramas whose quad table would not be reasonable to allocate.
+      const size_t entries = (size_t)(h + 1) * (w + 1);
+      fmt = (entries * 32 <= (size_t)384 << 20) ? PCL_IMAGE_F16D : (entries * 16 <= (size_t)4096 << 20) ? PCL_IMAGE_U8Q : PCL_IMAGE_TEX;
     }
   } else if (fmt != PCL_IMAGE_F32 && fmt != PCL_IMAGE_TEX) {
     pcl_set_error("unknown image format %d", format);
@@ -287,10 +289,17 @@ static int pcl_image_build(pcl_image* im, const float* img, int h, int w, int fo
     PCL_CUDA(pcl_pool_alloc(&im->data, im->bytes, st));
     grid.y = h + 1;
     if (format == PCL_IMAGE_AUTO) {      // compact companion table for small refinement batches (see pcl_common.cuh)
-      pcl_image_set_geometry(im->view_small, h, w, w + 1);
-      im->view_small.fmt = PCL_IMAGE_U8Q; im->view_small.tex_scale = 1.0f / 255.0f;
-      PCL_CUDA(pcl_pool_alloc(&im->data_small, (size_t)(h + 1) * (w + 1) * 16, st));
-      pcl_build_u8q_kernel<<<grid, block, 0, st>>>(img, h, w, (uint4*)im->data_small);
+      // quad entries (16 B) while that table is small (1024x2048: 33.5 MB); plain texels (4 B) for larger panoramas,
+      // where a sparse cloud's moving poses miss L2 and the smaller table wins (2048x4096, 1 M points: 52 vs 59 us)
+      const bool quad = (size_t)(h + 1) * (w + 1) * 16 <= ((size_t)48 << 20);
+      pcl_image_set_geometry(im->view_small, h, w, quad ? w + 1 : w + 2);
+      im->view_small.fmt = quad ? PCL_IMAGE_U8Q : PCL_IMAGE_U8P; im->view_small.tex_scale = 1.0f / 255.0f;
+      PCL_CUDA(pcl_pool_alloc(&im->data_small, quad ? (size_t)(h + 1) * (w + 1) * 16 : (size_t)(h + 2) * (w + 2) * 4, st));
+      if (quad) {
+        pcl_build_u8q_kernel<<<grid, block, 0, st>>>(img, h, w, (uint4*)im->data_small);
+      } else {
+        pcl_build_u8p_kernel<<<dim3(grid.x, h + 2), block, 0, st>>>(img, h, w, (unsigned int*)im->data_small);
+      }
       PCL_LAUNCH_CHECK();
       im->view_small.data = im->data_small;
       im->has_small = 1;

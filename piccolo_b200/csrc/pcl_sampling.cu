@@ -335,7 +335,7 @@ static cudaError_t pcl_launch_fmt(const PclLaunchPlan& pl, const PclCloudView& C
                                   double* partial, unsigned int* counters, const PclFinalize& fin, cudaStream_t st, bool pdl) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  const int swap = (!BWD && pl.gy > 1 && pl.gx <= 65535) ? pcl_env_int("PCL_SWAP", 0) : 0;
+  const int swap = (!BWD && pl.gy > 1 && pl.gx <= 65535) ? pcl_env_int("PCL_SWAP", 1) : 0;
   cfg.gridDim = swap ? dim3(pl.gy, pl.gx) : dim3(pl.gx, pl.gy);
   cfg.blockDim = dim3(PCL_THREADS);
   cfg.stream = st;
