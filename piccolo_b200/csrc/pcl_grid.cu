@@ -20,7 +20,7 @@
 #include <string.h>
 
 #define PCL_GRID_MAX_ROT 32
-#define PCL_GRID_TOL 2e-6       // third rows closer than this (fp64 from the fp32 angles) are the same group
+#define PCL_GRID_TOL 1e-6       // third rows closer than this (fp64 from the fp32 angles) are the same group
 
 struct PclGridPlan {
   int R, NG;
