@@ -13,6 +13,7 @@
  *   pcl_topk           `loss_table.flatten().argsort()[:num_input]`             (utils.py:501-502)
  *   pcl_loss_fwd_bwd   `SamplingLoss.forward` + autograd backward               (omniloc.py:171-202)
  *                      `BatchSamplingLoss.forward` + backward                   (omniloc.py:311-356)
+ *   pcl_color_*        `color_match` (per-query panorama preprocessing)                 (color_utils.py:146-234)
  *   pcl_refine_*       the optimisation loops of `omniloc` / `omniloc_batch`:
  *                      loss, backward, Adam.step, ReduceLROnPlateau.step, clamp (omniloc.py:44-58, :249-269)
  *
@@ -108,6 +109,18 @@ int pcl_topk(const float* loss_p_dev, int64_t p, int k, int64_t* idx_k_dev, void
  * panorama.  hist_intersect_k_dev[k] = the reference's `hist_intersect` (larger is better). */
 int pcl_hist_rerank(const pcl_cloud* c, const float* img_hw3_dev, int h, int w, const float* poses_k6_dev, int k,
                     int num_split_h, int num_split_w, float* hist_intersect_k_dev, void* stream);
+
+/* ---- colour matching of the panorama to the cloud (color_match, color_utils.py:146-234; localize.py:402-404) ------ */
+/* Both inputs must be uint8/255 data.  pcl_color_stats fills stats_dev (PCL_COLOR_STATS_BYTES, caller-allocated device
+ * memory): double whist[3][256] (histogram weighted by row_weight_h_dev[row] = sin(row/H*pi), color_utils.py:216-217, of the lit pixels by TRUNCATED level),
+ * uint32 level_cnt[3][256], uint32 value_cnt[3][256] (lit pixels by exact value k), uint64 cloud_cnt[3][256] (points by
+ * exact value k), int32 flags[2] (flags[0] != 0: an input was not exactly k/255).  The <= 256-entry cumulative sums and
+ * the reference's interpolation are done by the caller (piccolo_b200/color_utils.py); pcl_color_apply rewrites every lit
+ * pixel through the resulting look-up table lut[c][k]. */
+#define PCL_COLOR_STATS_BYTES (768 * 24 + 16)
+int pcl_color_stats(const float* img_hw3_dev, int h, int w, const float* row_weight_h_dev, const float* rgb_n3_dev, int64_t n,
+                    void* stats_dev, void* stream);
+int pcl_color_apply(const float* img_hw3_dev, int h, int w, const float* lut_3x256_dev, float* out_hw3_dev, void* stream);
 
 /* ---- loss + analytic 6-DoF gradient of B poses (autograd.Function backend) ------------------- */
 /* grad_b6_dev[b] = d loss_b / d (tx,ty,tz,yaw,pitch,roll) */

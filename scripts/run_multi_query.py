@@ -7,6 +7,7 @@ import os, sys, time
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from piccolo_b200 import engine, pipeline, synth
+from piccolo_b200.color_utils import color_match, requantize
 from piccolo_b200.dist import shard_bounds
 from piccolo_b200.utils import generate_rot_points, generate_trans_points, grid_poses
 
@@ -17,6 +18,7 @@ if ws > 1:
     dist.init_process_group("nccl", device_id=dev)
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 5_000_000
 Q = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+MATCH = os.environ.get("PCL_MATCH_COLOR", "1") == "1"
 H, W = 1024, 2048                                                  # localize.py:381 forces 2048x1024
 room = (8.0, 6.0, 3.0)
 xyz_np, rgb8 = synth.sample_room_points(N, room, seed=2)
@@ -36,6 +38,8 @@ def run_all():
     rows = []
     for gt, img_h in queries:
         img = img_h.to(dev, non_blocking=True)
+        if MATCH:                                                    # match_color=True of omniscenes.ini (localize.py:402-404):
+            img = requantize(color_match(img, rgb))                  # CDF matching on the device + the drivers' uint8 round trip
         out = pipeline.localize_query(cloud, engine.Image(img), grid, cfg, img=img)
         rows.append(torch.cat([out["pose"], out["loss"].reshape(1)]))
     return torch.stack(rows) if rows else torch.zeros((0, 7), device=dev)
@@ -63,6 +67,6 @@ if ws > 1:
 if rank == 0:
     evals = Q * pipeline.query_evals(N, len(grid), cfg)
     print(f"C4: ranks={ws} N={N} queries={Q} grid={len(grid)} poses: {dt:.3f} s total, {dt/Q*1e3:.1f} ms/query wall ({dt/max(1,hi-lo)*1e3:.1f} ms per query per GPU), "
-          f"{evals/dt/1e9:.1f} G pp/s aggregate; localised {int(stat[0])}/{int(stat[1])} (t<0.1 m, r<5 deg)")
+          f"{evals/dt/1e9:.1f} G pp/s aggregate; match_color={MATCH}; localised {int(stat[0])}/{int(stat[1])} (t<0.1 m, r<5 deg)")
 if ws > 1:
     dist.destroy_process_group()

@@ -394,3 +394,41 @@ def test_large_refinement_batch_matches_oracle(golden):
         err = np.abs(out["pose"].cpu().numpy() - o["pose"])
         assert (err < 3e-4).mean() >= 0.98 and err.max() < 5e-3, (err.max(), (err < 3e-4).mean())
         np.testing.assert_allclose(out["loss"].cpu().numpy(), o["loss"], rtol=2e-3)
+
+
+def test_color_match_on_device_matches_reference_and_host_path(golden):
+    """color_match (color_utils.py:146-234) through pcl_color_stats / pcl_color_apply: against the golden output of
+    the unmodified reference, and against the CPU restatement on a C4-style perturbed 1024x2048 panorama, where the
+    uint8 re-quantisation the driver applies next (localize.py:404) must come out identical."""
+    from piccolo_b200 import _lib
+    from piccolo_b200.color_utils import color_match
+    g = golden("color_small")
+    img, rgb = synth.img_from_u8(g["img8"]), synth.rgb_from_u8(g["rgb8"])
+    n0 = _lib.launch_count()
+    m = color_match(cu(img), cu(rgb))
+    assert m.is_cuda and _lib.launch_count() - n0 == 3                      # two statistics passes + the rewrite
+    np.testing.assert_allclose(m.cpu().numpy(), g["match_img"], atol=2e-6)
+    assert ((255 * m.cpu().numpy()).astype(np.uint8) != (255 * g["match_img"]).astype(np.uint8)).mean() < 1e-3
+    host = color_match(torch.from_numpy(img), torch.from_numpy(rgb)).numpy()
+    np.testing.assert_array_equal(m.cpu().numpy(), host)
+    # C4-sized: perturbed query panorama against a 1 M-point cloud
+    room = (8.0, 6.0, 3.0)
+    xyz, rgb8 = synth.sample_room_points(1_000_000, room, seed=2)
+    gt = synth.random_gt_pose(room, seed=101, yaw_only=True)
+    pano8 = synth.perturb_panorama(synth.render_panorama(gt, 1024, 2048, room), seed=3, gamma=1.1, wb=(1.0, 0.97, 1.02), retexture_frac=0.1)
+    img, rgb = synth.img_from_u8(pano8), synth.rgb_from_u8(rgb8)
+    dev_out = color_match(cu(img), cu(rgb)).cpu().numpy()
+    host_out = color_match(torch.from_numpy(img), torch.from_numpy(rgb)).numpy()
+    np.testing.assert_allclose(dev_out, host_out, atol=2e-7)
+    np.testing.assert_array_equal((255 * dev_out).astype(np.uint8), (255 * host_out).astype(np.uint8))
+    assert np.array_equal(dev_out[:64], img[:64])                           # the black caps are not lit: untouched
+    from piccolo_b200 import engine
+    from piccolo_b200.color_utils import requantize
+    rq = requantize(cu(dev_out))                                            # the drivers' uint8 round trip, on the device
+    np.testing.assert_array_equal(rq.cpu().numpy(), (255 * dev_out).astype(np.uint8).astype(np.float32) / np.float32(255.0))
+    assert engine.Image(rq).format == engine.IMAGE_F16D                     # exactly k/255: the uint8 texel tables apply
+    # inputs that are not uint8/255 data take the CPU restatement (same result as calling it on CPU tensors)
+    noisy = img.copy(); noisy[100, 100, 0] += 1e-3
+    a = color_match(cu(noisy), cu(rgb)).cpu().numpy()
+    b = color_match(torch.from_numpy(noisy), torch.from_numpy(rgb)).numpy()
+    np.testing.assert_array_equal(a, b)
