@@ -13,7 +13,7 @@
  *   pcl_topk           `loss_table.flatten().argsort()[:num_input]`             (utils.py:501-502)
  *   pcl_loss_fwd_bwd   `SamplingLoss.forward` + autograd backward               (omniloc.py:171-202)
  *                      `BatchSamplingLoss.forward` + backward                   (omniloc.py:311-356)
- *   pcl_color_*        `color_match` (per-query panorama preprocessing)                 (color_utils.py:146-234)
+ *   pcl_color_*        `color_match`, `color_mod` (per-query colour preprocessing)      (color_utils.py:146-234, :7-65)
  *   pcl_refine_*       the optimisation loops of `omniloc` / `omniloc_batch`:
  *                      loss, backward, Adam.step, ReduceLROnPlateau.step, clamp (omniloc.py:44-58, :249-269)
  *
@@ -121,6 +121,16 @@ int pcl_hist_rerank(const pcl_cloud* c, const float* img_hw3_dev, int h, int w, 
 int pcl_color_stats(const float* img_hw3_dev, int h, int w, const float* row_weight_h_dev, const float* rgb_n3_dev, int64_t n,
                     void* stats_dev, void* stream);
 int pcl_color_apply(const float* img_hw3_dev, int h, int w, const float* lut_3x256_dev, float* out_hw3_dev, void* stream);
+
+/* ---- joint luma equalisation of panorama and cloud (color_mod, color_utils.py:7-65; localize.py:173-179, :405-410) -- */
+/* hist_2xbins_dev: uint64 [2][num_bins] luma-bin counts of the lit pixels and of the points (8-bit YCrCb, cv2's fixed-point
+ * conversion restated in integers).  The caller forms the cumulative distribution (num_bins floats,
+ * piccolo_b200/color_utils.py); pcl_color_mod_apply replaces the luma of every lit pixel and every point by cdf[bin] and
+ * converts back, with the reference's uint8 truncations. */
+int pcl_color_mod_stats(const float* img_hw3_dev, int h, int w, const float* rgb_n3_dev, int64_t n, int num_bins,
+                        unsigned long long* hist_2xbins_dev, void* stream);
+int pcl_color_mod_apply(const float* img_hw3_dev, int h, int w, const float* rgb_n3_dev, int64_t n, int num_bins,
+                        const float* cdf_bins_dev, float* out_img_hw3_dev, float* out_rgb_n3_dev, void* stream);
 
 /* ---- loss + analytic 6-DoF gradient of B poses (autograd.Function backend) ------------------- */
 /* grad_b6_dev[b] = d loss_b / d (tx,ty,tz,yaw,pitch,roll) */

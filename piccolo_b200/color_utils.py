@@ -1,6 +1,8 @@
 """Per-query colour preprocessing of the reference (`color_utils.py:7-65` color_mod, `:146-234` color_match),
-restated with numpy + cv2.  Host-side, once per query, not on the sampling-loss path;
-both keep the reference's side effect that outputs are re-quantised through uint8."""
+SURVEY §8f next #4.  CUDA tensors are processed on the device (pcl_color.cu: histogram and rewrite passes; the
+<= 256-entry table arithmetic stays here and is shared with the numpy + cv2 restatement used for CPU tensors, which is
+pinned to the reference's golden outputs); both keep the reference's side effect that outputs are re-quantised
+through uint8."""
 from __future__ import annotations
 
 import cv2
@@ -23,18 +25,46 @@ def _to_rgb(unit_ycc: np.ndarray) -> np.ndarray:
     return cv2.cvtColor(u8, cv2.COLOR_YCR_CB2RGB).reshape(-1, 3).astype(np.float32) / np.float32(255.0)
 
 
+def _equalise_cdf(hist_img: np.ndarray, hist_pts: np.ndarray) -> np.ndarray:
+    """cumulative distribution of the joint luma histogram (color_utils.py:38-47): `.float()` each, add, normalise,
+    cumsum — all in fp32.  Shared by the CPU and the CUDA path."""
+    hist = hist_img.astype(np.float32) + hist_pts.astype(np.float32)
+    return np.cumsum(hist / hist.sum(), dtype=np.float32)
+
+
+def _color_mod_cuda(img: torch.Tensor, rgb: torch.Tensor, num_bins: int):
+    """CUDA path (pcl_color.cu): luma-bin histograms on the device, the num_bins-entry cumulative sum here, one
+    rewrite pass over pixels and points on the device."""
+    from . import _lib
+    from .engine import _f32c, _stream
+    lib = _lib.load()
+    H, W, _ = img.shape
+    im, pts = _f32c(img), _f32c(rgb)
+    hist = torch.empty(2 * num_bins, dtype=torch.int64, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.check(lib.pcl_color_mod_stats(im.data_ptr(), H, W, pts.data_ptr(), pts.shape[0], num_bins, hist.data_ptr(), _stream(img.device)))
+    h = hist.cpu().numpy()                                          # synchronises
+    cdf = torch.from_numpy(_equalise_cdf(h[:num_bins], h[num_bins:])).to(img.device)
+    out_img, out_rgb = torch.empty_like(im), torch.empty_like(pts)
+    with torch.cuda.device(img.device):
+        _lib.check(lib.pcl_color_mod_apply(im.data_ptr(), H, W, pts.data_ptr(), pts.shape[0], num_bins, cdf.data_ptr(), out_img.data_ptr(),
+                                           out_rgb.data_ptr(), _stream(img.device)))
+    return out_img, out_rgb
+
+
 def color_mod(img: torch.Tensor, rgb: torch.Tensor, num_bins: int):
     """Joint histogram equalisation of the luma of panorama and cloud (YCrCb), `sharpen_color` of the configs.
-    Returns (img (H,W,3), rgb (N,3)) float32 on img.device."""
+    Returns (img (H,W,3), rgb (N,3)) float32 on img.device.  CUDA tensors are processed on the device."""
     device = img.device
     H, W, _ = img.shape
+    if img.is_cuda and rgb.is_cuda and 2 <= num_bins <= 4096:
+        return _color_mod_cuda(img.detach(), rgb.detach(), int(num_bins))
     flat = img.detach().cpu().numpy().astype(np.float32).reshape(-1, 3).copy()
     lit = _lit_mask(flat)
     ycc_img, ycc_pts = _to_ycc(flat[lit]), _to_ycc(rgb.detach().cpu().numpy().astype(np.float32))
     scale = np.float32(num_bins - 1)
     bin_img, bin_pts = (ycc_img[:, 0] * scale).astype(np.int64), (ycc_pts[:, 0] * scale).astype(np.int64)
-    hist = (np.bincount(bin_img, minlength=num_bins) + np.bincount(bin_pts, minlength=num_bins)).astype(np.float32)
-    cdf = np.cumsum(hist / hist.sum(), dtype=np.float32)
+    cdf = _equalise_cdf(np.bincount(bin_img, minlength=num_bins), np.bincount(bin_pts, minlength=num_bins))
     ycc_img[:, 0] = cdf[bin_img]
     ycc_pts[:, 0] = cdf[bin_pts]
     flat[lit] = _to_rgb(ycc_img)

@@ -125,3 +125,95 @@ extern "C" int pcl_color_apply(const float* img_hw3_dev, int h, int w, const flo
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// color_mod (`sharpen_color`, color_utils.py:7-65; localize.py:173-179, :405-410): joint histogram equalisation of
+// the luma of panorama and cloud in 8-bit YCrCb.  The reference goes through cv2.cvtColor on uint8 data; its
+// fixed-point conversion (yuv_shift 14, coefficients 4899/9617/1868, 11682/9241, 22987/-11698/-5636/29049, delta
+// 128) is restated here in integers — checked against cv2 for all 2^24 triples in both directions
+// (tests/test_host_logic.py).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pcl_sat8(int v) { return min(max(v, 0), 255); }
+
+struct PclYcc { int y, cr, cb; };
+
+// (colour * 255.).astype(uint8) -> cv2.COLOR_RGB2YCR_CB
+__device__ __forceinline__ PclYcc pcl_rgb_to_ycc(float rf, float gf, float bf) {
+  const int r = (int)(unsigned char)(rf * 255.0f), g = (int)(unsigned char)(gf * 255.0f), b = (int)(unsigned char)(bf * 255.0f);
+  PclYcc o;
+  o.y = pcl_sat8((r * 4899 + g * 9617 + b * 1868 + (1 << 13)) >> 14);
+  o.cr = pcl_sat8(((r - o.y) * 11682 + (128 << 14) + (1 << 13)) >> 14);
+  o.cb = pcl_sat8(((b - o.y) * 9241 + (128 << 14) + (1 << 13)) >> 14);
+  return o;
+}
+
+// luma bin: ((u8 / 255.) * (num_bins - 1)).long()   (color_utils.py:38-39)
+__device__ __forceinline__ int pcl_luma_bin(int y, float scale) { return (int)(((float)y / 255.0f) * scale); }
+
+__global__ void pcl_color_mod_stats_kernel(const float* __restrict__ img, const long long npix, const float* __restrict__ rgb, const long long n,
+                                           const int num_bins, unsigned long long* __restrict__ hist /*[2][num_bins]: image, cloud*/) {
+  extern __shared__ unsigned int s_h[];       // [2][num_bins]
+  for (int i = threadIdx.x; i < 2 * num_bins; i += blockDim.x) s_h[i] = 0u;
+  __syncthreads();
+  const float scale = (float)(num_bins - 1);
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (long long p = t0; p < npix; p += stride) {
+    const float r = img[3 * p], g = img[3 * p + 1], b = img[3 * p + 2];
+    if (!pcl_color_lit(r, g, b)) continue;
+    atomicAdd(&s_h[pcl_luma_bin(pcl_rgb_to_ycc(r, g, b).y, scale)], 1u);
+  }
+  for (long long p = t0; p < n; p += stride)
+    atomicAdd(&s_h[num_bins + pcl_luma_bin(pcl_rgb_to_ycc(rgb[3 * p], rgb[3 * p + 1], rgb[3 * p + 2]).y, scale)], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * num_bins; i += blockDim.x) if (s_h[i]) atomicAdd(hist + i, (unsigned long long)s_h[i]);
+}
+
+// equalised luma -> (ycc * 255.).astype(uint8) -> cv2.COLOR_YCR_CB2RGB -> / 255.
+__device__ __forceinline__ void pcl_color_mod_one(float r, float g, float b, const float* __restrict__ cdf, float scale, float* out) {
+  const PclYcc c = pcl_rgb_to_ycc(r, g, b);
+  const int y = (int)(unsigned char)(__ldg(cdf + pcl_luma_bin(c.y, scale)) * 255.0f);
+  const int cr = (int)(unsigned char)(((float)c.cr / 255.0f) * 255.0f) - 128, cb = (int)(unsigned char)(((float)c.cb / 255.0f) * 255.0f) - 128;
+  out[0] = (float)pcl_sat8(y + ((cr * 22987 + (1 << 13)) >> 14)) / 255.0f;
+  out[1] = (float)pcl_sat8(y + ((cb * -5636 + cr * -11698 + (1 << 13)) >> 14)) / 255.0f;
+  out[2] = (float)pcl_sat8(y + ((cb * 29049 + (1 << 13)) >> 14)) / 255.0f;
+}
+
+__global__ void pcl_color_mod_apply_kernel(const float* __restrict__ img, const long long npix, const float* __restrict__ rgb, const long long n,
+                                           const int num_bins, const float* __restrict__ cdf, float* __restrict__ out_img, float* __restrict__ out_rgb) {
+  const float scale = (float)(num_bins - 1);
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (long long p = t0; p < npix; p += stride) {
+    const float r = img[3 * p], g = img[3 * p + 1], b = img[3 * p + 2];
+    if (pcl_color_lit(r, g, b)) pcl_color_mod_one(r, g, b, cdf, scale, out_img + 3 * p);
+    else { out_img[3 * p] = r; out_img[3 * p + 1] = g; out_img[3 * p + 2] = b; }
+  }
+  for (long long p = t0; p < n; p += stride) pcl_color_mod_one(rgb[3 * p], rgb[3 * p + 1], rgb[3 * p + 2], cdf, scale, out_rgb + 3 * p);
+}
+
+extern "C" int pcl_color_mod_stats(const float* img_hw3_dev, int h, int w, const float* rgb_n3_dev, int64_t n, int num_bins,
+                                   unsigned long long* hist_2xbins_dev, void* stream) {
+  if (!img_hw3_dev || !rgb_n3_dev || !hist_2xbins_dev || h < 1 || w < 1 || n < 1 || num_bins < 2 || num_bins > 4096) {
+    pcl_set_error("bad colour-equalisation arguments (num_bins must be 2..4096)");
+    return PCL_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  PCL_CUDA(cudaMemsetAsync(hist_2xbins_dev, 0, (size_t)2 * num_bins * sizeof(unsigned long long), st));
+  const long long m = (long long)h * w > n ? (long long)h * w : n;
+  pcl_color_mod_stats_kernel<<<pcl_color_blocks(m), 256, (size_t)2 * num_bins * sizeof(unsigned int), st>>>(img_hw3_dev, (long long)h * w, rgb_n3_dev, n,
+                                                                                                           num_bins, hist_2xbins_dev);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
+
+extern "C" int pcl_color_mod_apply(const float* img_hw3_dev, int h, int w, const float* rgb_n3_dev, int64_t n, int num_bins,
+                                   const float* cdf_bins_dev, float* out_img_hw3_dev, float* out_rgb_n3_dev, void* stream) {
+  if (!img_hw3_dev || !rgb_n3_dev || !cdf_bins_dev || !out_img_hw3_dev || !out_rgb_n3_dev || h < 1 || w < 1 || n < 1 || num_bins < 2) {
+    pcl_set_error("bad colour-equalisation arguments");
+    return PCL_ERR_INVALID;
+  }
+  const long long m = (long long)h * w > n ? (long long)h * w : n;
+  pcl_color_mod_apply_kernel<<<pcl_color_blocks(m), 256, 0, (cudaStream_t)stream>>>(img_hw3_dev, (long long)h * w, rgb_n3_dev, n, num_bins, cdf_bins_dev,
+                                                                                    out_img_hw3_dev, out_rgb_n3_dev);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}

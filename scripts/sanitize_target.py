@@ -23,5 +23,8 @@ for order in (0, 1):
         out = engine.Refiner(6, 0.1, 0.8, 5, True).reset(poses[:6]).run(cloud, image, 4).read()
     idx = engine.topk(loss, 10)
     s = engine.hist_rerank(cloud, img, poses[:12], 4, 4)
+from piccolo_b200.color_utils import color_match, color_mod
+cm = color_match(img, rgb)
+mi, mr = color_mod(img, rgb, 256)
 torch.cuda.synchronize()
 print("sanitize target ok", float(loss.min()), idx[:3].tolist(), float(s.max()))

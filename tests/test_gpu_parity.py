@@ -432,3 +432,22 @@ def test_color_match_on_device_matches_reference_and_host_path(golden):
     a = color_match(cu(noisy), cu(rgb)).cpu().numpy()
     b = color_match(torch.from_numpy(noisy), torch.from_numpy(rgb)).numpy()
     np.testing.assert_array_equal(a, b)
+
+
+def test_color_mod_on_device_matches_reference_and_host_path(golden):
+    """color_mod (color_utils.py:7-65) through pcl_color_mod_stats / pcl_color_mod_apply: bit-exact against the golden
+    output of the unmodified reference (cv2's integer YCrCb restated in integers) and against the CPU restatement at
+    full size, for 256 and 64 luma bins."""
+    from piccolo_b200.color_utils import color_mod
+    g = golden("color_small")
+    img, rgb = synth.img_from_u8(g["img8"]), synth.rgb_from_u8(g["rgb8"])
+    a_img, a_rgb = color_mod(cu(img), cu(rgb), 256)
+    assert a_img.is_cuda and a_rgb.is_cuda
+    np.testing.assert_array_equal(a_img.cpu().numpy(), g["mod_img"])
+    np.testing.assert_array_equal(a_rgb.cpu().numpy(), g["mod_rgb"])
+    sc = synth.make_scene(1_000_000, 1024, 2048, seed=3)
+    for bins in (256, 64):
+        d_img, d_rgb = color_mod(cu(sc.img), cu(sc.rgb), bins)
+        h_img, h_rgb = color_mod(torch.from_numpy(sc.img), torch.from_numpy(sc.rgb), bins)
+        np.testing.assert_array_equal(d_img.cpu().numpy(), h_img.numpy())
+        np.testing.assert_array_equal(d_rgb.cpu().numpy(), h_rgb.numpy())

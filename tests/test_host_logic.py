@@ -95,3 +95,30 @@ def test_candidate_grids_match_reference(golden):
         # the reference's order comes out of a python set (PYTHONHASHSEED dependent): compare as sets of rotations
         key = lambda a: sorted(tuple(np.round(r, 5)) for r in a)
         assert key(rot) == key(ref)
+
+
+def test_integer_ycrcb_matches_cv2():
+    """The fixed-point 8-bit RGB <-> YCrCb conversion that pcl_color.cu restates in integers, against cv2.cvtColor
+    (the reference's color_mod goes through it, color_utils.py:30-33, :51, :62) on 2^22 triples incl. all extremes."""
+    import cv2
+
+    def rgb2ycc(u8):
+        r, g, b = [u8[..., i].astype(np.int32) for i in range(3)]
+        y = (r * 4899 + g * 9617 + b * 1868 + (1 << 13)) >> 14
+        cr = ((r - y) * 11682 + (128 << 14) + (1 << 13)) >> 14
+        cb = ((b - y) * 9241 + (128 << 14) + (1 << 13)) >> 14
+        return np.stack([np.clip(y, 0, 255), np.clip(cr, 0, 255), np.clip(cb, 0, 255)], -1).astype(np.uint8)
+
+    def ycc2rgb(u8):
+        y, cr, cb = [u8[..., i].astype(np.int32) for i in range(3)]
+        b = y + (((cb - 128) * 29049 + (1 << 13)) >> 14)
+        g = y + (((cb - 128) * -5636 + (cr - 128) * -11698 + (1 << 13)) >> 14)
+        r = y + (((cr - 128) * 22987 + (1 << 13)) >> 14)
+        return np.stack([np.clip(r, 0, 255), np.clip(g, 0, 255), np.clip(b, 0, 255)], -1).astype(np.uint8)
+
+    rng = np.random.default_rng(0)
+    tri = rng.integers(0, 256, (1, 1 << 22, 3), dtype=np.uint8)
+    edge = np.array([[a, b, c] for a in (0, 1, 127, 128, 254, 255) for b in (0, 1, 127, 128, 254, 255) for c in (0, 1, 127, 128, 254, 255)], np.uint8)
+    tri[0, :len(edge)] = edge
+    np.testing.assert_array_equal(cv2.cvtColor(tri, cv2.COLOR_RGB2YCR_CB), rgb2ycc(tri))
+    np.testing.assert_array_equal(cv2.cvtColor(tri, cv2.COLOR_YCR_CB2RGB), ycc2rgb(tri))
