@@ -83,6 +83,8 @@ struct pcl_refine {
   size_t partial_floats;
   unsigned int* counters;       // last-block-done tickets
   float* loss;                  // [B]
+  double* bc_dev;               // grow-only: per-iteration Adam bias corrections of a persistent run, [num_iter][2]
+  size_t bc_cap;
 };
 
 struct PclCloudView {

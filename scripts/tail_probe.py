@@ -1,0 +1,20 @@
+"""Per-iteration overhead of the fused refinement launch: the loop on a cloud so small that the main loop vanishes."""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.getcwd())
+from piccolo_b200 import engine, synth
+from scripts.perf_probe import timeit
+dev = torch.device("cuda:0")
+for n in (4096, 65536, 262144, 1_000_000):
+    sc = synth.make_scene(n, 1024, 2048, seed=3)
+    xyz, rgb, img = [torch.from_numpy(a).to(dev) for a in (sc.xyz, sc.rgb, sc.img)]
+    cloud, image = engine.Cloud(xyz, rgb), engine.Image(img)
+    rng = np.random.default_rng(0)
+    starts = torch.from_numpy(np.stack([sc.gt_pose + np.concatenate([rng.normal(0, 0.2, 3), rng.normal(0, 0.1, 3)]) for _ in range(6)]).astype(np.float32)).to(dev)
+    ref = engine.Refiner(6, 0.1, 0.8, 5, True)
+    def run():
+        ref.reset(starts); ref.run(cloud, image, 100)
+    for pdl in ("1", "0"):
+        os.environ["PCL_PDL"] = pdl
+        ms = timeit(run, iters=3, warm=1)
+        print(f"N={n}: {ms*10:.2f} us per iteration (PDL={pdl})", flush=True)
