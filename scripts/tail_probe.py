@@ -14,7 +14,7 @@ for n in (4096, 65536, 262144, 1_000_000):
     ref = engine.Refiner(6, 0.1, 0.8, 5, True)
     def run():
         ref.reset(starts); ref.run(cloud, image, 100)
-    for pdl in ("1", "0"):
-        os.environ["PCL_PDL"] = pdl
+    for persist in ("0", "1"):
+        os.environ["PCL_PERSIST"] = persist
         ms = timeit(run, iters=3, warm=1)
-        print(f"N={n}: {ms*10:.2f} us per iteration (PDL={pdl})", flush=True)
+        print(f"N={n}: {ms*10:.2f} us per iteration (persistent={persist})", flush=True)
