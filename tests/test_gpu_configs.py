@@ -178,13 +178,14 @@ def test_main_cli_writes_reference_outputs(tmp_path):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_sharded_single_query_on_two_gpus():
-    """Config C3 path over NCCL: one query sharded over 2 ranks gives the single-GPU candidate set and pose."""
+    """Config C3 path over NCCL: one query (the bench's scene and 75 x 24 start grid) sharded over 2 ranks gives the
+    single-GPU candidate set, winner and pose."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29533", os.path.join(root, "scripts", "run_sharded_query.py"), "2000000", "1024", "12"],
+                        "--master-port", "29533", os.path.join(root, "scripts", "run_sharded_query.py"), "1000000", "1024", "12", "stanford"],
                        cwd=root, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
     assert "same candidate set=True" in r.stdout
