@@ -223,7 +223,10 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if ws > 1:
-        # NCCL prints its version banner (debug levels VERSION and WARN) to STDOUT; stdout carries exactly one JSON line
+        # NCCL prints its version banner (debug levels VERSION and WARN) to STDOUT, and honours NCCL_DEBUG_FILE only above
+        # level VERSION; stdout carries exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     _lib.load()
