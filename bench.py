@@ -143,37 +143,6 @@ def cpu_port_sample(sc, grid_cpu, cfg, n_score, n_iter, threads=None):
     return {"evals": evals, "seconds": t2 - t0, "score_s": t1 - t0, "refine_s": t2 - t1}
 
 
-def aten_gpu_sample(sc, grid_poses, cfg, device, n_score=200, n_iter=20):
-    """Optional extra baseline (`--aten-gpu-baseline`, off by default): the reference's own op chain (the oracle's
-    ATen-chain port: einsum, atan2, grid_sample, autograd, torch.optim.Adam + ReduceLROnPlateau) executed by PyTorch
-    ON THE SAME B200 — the same-box kernels to beat.  Bounded sample like the CPU baseline."""
-    from oracle import piccolo_oracle as orc
-    xyz, rgb, img = [torch.from_numpy(a).to(device) for a in (sc.xyz, sc.rgb, sc.img)]
-    poses = grid_poses.to(device)
-    n = xyz.shape[0]
-
-    def score(k):
-        with torch.no_grad():
-            for i in range(k):
-                orc.sampling_loss_torch(xyz, rgb, img, poses[i:i + 1])      # one pose per call, as the loop of utils.py:484-499
-
-    def refine(k):
-        orc.refine_torch(xyz, rgb, img, poses[: cfg.num_input].clone(), lr=cfg.lr, num_iter=k, patience=cfg.patience, factor=cfg.factor,
-                         q=cfg.out_of_room_quantile, batch_semantics=bool(cfg.parallel))
-    score(3); refine(2)
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    score(n_score)
-    torch.cuda.synchronize(); t1 = time.perf_counter()
-    refine(n_iter)
-    torch.cuda.synchronize(); t2 = time.perf_counter()
-    P = poses.shape[0]
-    return {"kind": "reference op chain (oracle ATen-chain port) run by PyTorch on cuda:0 of the same box", "unit": UNIT,
-            "score_evals_per_s": n * n_score / (t1 - t0), "refine_evals_per_s": n * n_iter * cfg.num_input / (t2 - t1),
-            "value": n * (n_score + n_iter * cfg.num_input) / (t2 - t0),
-            "sec_per_query_extrapolated": (t1 - t0) / n_score * P + (t2 - t1) / n_iter * cfg.num_iter,
-            "sample": f"{n_score} of {P} grid poses forward-only + {n_iter} of {cfg.num_iter} refinement iterations (B={cfg.num_input})"}
-
-
 def run_reference(args):
     """`--impl reference`: the reference's CPU implementation of the path (the oracle port; the reference is
     pure Python and cannot travel to the GPU box) on the host cores, same config/metric/unit."""
@@ -349,8 +318,6 @@ def run_ours(args):
                                     "sample": f"24 of {P} grid poses forward-only ({r['score_s']:.1f} s) + 2 of {cfg.num_iter} refinement iterations B={cfg.num_input} "
                                               f"({r['refine_s']:.1f} s) of the same workload, oracle ATen-chain port, {torch.get_num_threads()} threads",
                                     "sec_per_query_extrapolated": q_evals / (r["evals"] / r["seconds"])}
-        if ws == 1 and args.aten_gpu_baseline:
-            line["aten_gpu_baseline"] = aten_gpu_sample(sc, grid.poses(), cfg, device)
         # `roofline` = the kernel with the larger share of the step (ncu launch list: profiles/r1_launch_list_bench_C2.md); the two
         # phases are within a few per cent of each other at C2, so a near-tie goes to the refinement kernel (the lower fraction)
         line["roofline"] = dict(line["roofline_score"] if sum(score_ms) > 1.1 * sum(refine_ms) else line["roofline_refine"])
@@ -368,7 +335,6 @@ def main():
     ap.add_argument("--n-points", type=int, default=1_000_000)
     ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--aten-gpu-baseline", action="store_true", help="also time the reference's op chain run by PyTorch on cuda:0 (baseline only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
