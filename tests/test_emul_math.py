@@ -71,3 +71,56 @@ def test_emulated_structured_grid_matches_reference_losses(golden):
         lib.emul_grid(xyz.ctypes.data_as(fp), rgb.ctypes.data_as(fp), ctypes.c_long(len(xyz)), img.ctypes.data_as(fp), img.shape[0], img.shape[1],
                       base.ctypes.data_as(fp), delta.ctypes.data_as(fp), R, loss.ctypes.data_as(fp), cnt.ctypes.data_as(fp))
         np.testing.assert_allclose(loss, g["loss_table"][ti * R:(ti + 1) * R], rtol=2e-5)
+
+
+def _group_rotations(rot, tol=1e-6):
+    """numpy mirror of pcl_grid_plan_kernel (pcl_grid.cu): greedy grouping on the third row of R, delta from R_j R_b^T"""
+    from oracle import piccolo_oracle as orc
+    Rs = [orc.rot_and_derivs_np(r.astype(np.float64), np.float64)[0] for r in rot]
+    bases, groups = [], []
+    for j, R in enumerate(Rs):
+        for g, b in enumerate(bases):
+            if np.abs(R[2] - Rs[b][2]).max() < tol:
+                groups[g].append(j)
+                break
+        else:
+            bases.append(j); groups.append([j])
+    out = []
+    for b, members in zip(bases, groups):
+        deltas = []
+        for j in members:
+            M = Rs[j] @ Rs[b].T
+            assert np.abs(M - np.array([[M[0, 0], -M[1, 0], 0], [M[1, 0], M[0, 0], 0], [0, 0, 1]])).max() < 5e-6     # a turn about z
+            deltas.append(0.0 if j == b else np.arctan2(M[1, 0], M[0, 0]))
+        out.append((b, members, np.asarray(deltas, np.float32)))
+    return out
+
+
+def test_emulated_structured_grid_on_the_euler_lattice(golden):
+    """The 24 distinct rotations of the reference's 4x4x4 Euler lattice (utils.py:326-360) are 6 groups of 4 rotations
+    related by an in-plane turn; evaluating each group through pcl_grid_base / pcl_grid_member reproduces the oracle's
+    per-pose fp64 losses to the 1e-4 gate (measured ~1e-6) for every member."""
+    from oracle import piccolo_oracle as orc
+    from piccolo_b200 import utils as pu
+    small = golden("loss_small")
+    rgb, img = synth.rgb_from_u8(small["rgb8"]), synth.img_from_u8(small["img8"])
+    xyz = np.ascontiguousarray(small["xyz"], dtype=np.float32)
+    rot = pu.generate_rot_points({"yaw_only": False, "num_yaw": 4, "num_pitch": 4, "num_roll": 4}).numpy()
+    groups = _group_rotations(rot)
+    assert len(rot) == 24 and sorted(len(m) for _, m, _ in groups) == [4] * 6
+    yaw8 = pu.generate_rot_points({"yaw_only": True, "num_yaw": 8}).numpy()
+    assert [len(m) for _, m, _ in _group_rotations(yaw8)] == [8]
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", SRC, "-o", SO])
+    lib = ctypes.CDLL(SO)
+    fp = ctypes.POINTER(ctypes.c_float)
+    t = (xyz.min(0) + (xyz.max(0) - xyz.min(0)) * np.array([0.4, 0.55, 0.5])).astype(np.float32)
+    worst = 0.0
+    for b, members, delta in groups:
+        base = np.concatenate([t, rot[b]]).astype(np.float32)
+        loss, cnt = np.zeros(len(members), np.float32), np.zeros(len(members), np.float32)
+        lib.emul_grid(xyz.ctypes.data_as(fp), rgb.ctypes.data_as(fp), ctypes.c_long(len(xyz)), img.ctypes.data_as(fp), img.shape[0], img.shape[1],
+                      base.ctypes.data_as(fp), delta.ctypes.data_as(fp), len(members), loss.ctypes.data_as(fp), cnt.ctypes.data_as(fp))
+        for k, j in enumerate(members):
+            want = orc.loss_and_grad_np(xyz, rgb, img, np.concatenate([t, rot[j]]).astype(np.float64), np.float64, want_grad=False)[0]
+            worst = max(worst, abs(loss[k] - want) / want)
+    assert worst < 1e-4, worst

@@ -122,3 +122,25 @@ def test_integer_ycrcb_matches_cv2():
     tri[0, :len(edge)] = edge
     np.testing.assert_array_equal(cv2.cvtColor(tri, cv2.COLOR_RGB2YCR_CB), rgb2ycc(tri))
     np.testing.assert_array_equal(cv2.cvtColor(tri, cv2.COLOR_YCR_CB2RGB), ycc2rgb(tri))
+
+
+def test_start_grid_indexing_matches_flat_pose_list():
+    """pipeline.StartGrid: pose index i*R+j (utils.py:484-485), row slices for sharding, selection by flat index."""
+    from piccolo_b200.pipeline import StartGrid
+    from piccolo_b200.utils import grid_poses
+    rng = np.random.default_rng(0)
+    trans, rot = torch.from_numpy(rng.normal(size=(7, 3)).astype(np.float32)), torch.from_numpy(rng.normal(size=(5, 3)).astype(np.float32))
+    g = StartGrid(trans, rot)
+    flat = grid_poses(trans, rot)
+    assert len(g) == 35 and torch.equal(g.poses(), flat)
+    idx = torch.tensor([0, 34, 12, 5, 29])
+    assert torch.equal(g.index_select(0, idx), flat.index_select(0, idx))
+    assert torch.equal(g.rows(2, 5).poses(), flat[2 * 5: 5 * 5])
+    assert g.to("cpu").trans.data_ptr() == g.trans.data_ptr()
+
+
+def test_requantize_is_the_drivers_uint8_round_trip():
+    from piccolo_b200.color_utils import requantize
+    x = torch.rand(64, 128, 3)
+    want = torch.from_numpy((255 * x.numpy()).astype(np.uint8)).float() / 255.
+    assert torch.equal(requantize(x), want)
