@@ -297,7 +297,10 @@ def run_ours(args):
                                 "bound": "hbm", "achieved": bwd_achieved, "peak": peak, "unit": "GB/s", "frac": bwd_achieved / peak,
                                 "traffic": ncu_traffic("C2_refine_launch_bytes") if default_size else None,
                                 "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_EVAL * cfg.num_input * args.n_points,
-                                "launch_us": bwd_launch_s * 1e6, "evals_per_s": cfg.num_input * args.n_points / bwd_launch_s},
+                                "launch_us": bwd_launch_s * 1e6, "evals_per_s": cfg.num_input * args.n_points / bwd_launch_s,
+                                "iterations_per_launch": cfg.num_iter,
+                                "note": "one cooperative launch runs all iterations; achieved / algorithmic bytes / traffic / launch_us are per iteration "
+                                        "(launch duration / num_iter, CUDA events around the launch)"},
             "roofline_score": {"kernel": "pcl_grid_score_kernel<fmt> (structured-grid forward-only scoring, one launch for the 75x24 start grid; rotations related "
                                          "by an in-plane turn share transform/elevation/azimuth per point)", "bound": "hbm",
                                "achieved": sc_achieved, "peak": peak, "unit": "GB/s", "frac": sc_achieved / peak,
