@@ -143,7 +143,9 @@ int pcl_loss_fwd_bwd(const pcl_cloud* c, const pcl_image* im, const float* poses
 int pcl_refine_create(int b, double lr, double factor, int patience, int batch_semantics, pcl_refine** out);
 /* load B start poses and reset Adam / plateau state */
 int pcl_refine_reset(pcl_refine* r, const float* poses_b6_dev, void* stream);
-/* run num_iter iterations: each is ONE kernel = loss + backward + reduction + Adam + plateau + clamp */
+/* run num_iter iterations: each is ONE kernel = loss + backward + reduction + Adam + plateau + clamp; batches of <= 16
+ * candidates run ALL iterations in one cooperative launch (cudaLaunchCooperativeKernel: one grid barrier per iteration),
+ * with the per-iteration launches as fallback where the device refuses it (PCL_PERSIST=0 forces the fallback) */
 int pcl_refine_run(pcl_refine* r, const pcl_cloud* c, const pcl_image* im, int num_iter, void* stream);
 /* pose_b6_dev: what the reference returns (clamped parameter, or the un-clamped copy under batch
  * semantics); param_b6_dev (nullable): Adam's clamped parameter; loss_b_dev: loss of the LAST forward;
