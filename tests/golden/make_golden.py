@@ -52,7 +52,30 @@ def ref_loss_grad(ref_omniloc, xyz, rgb, img, pose, dtype):
     return float(loss), g.astype(np.float64)
 
 
+def make_score_lattice(ref_omniloc, ref_utils):
+    """fixture 2d: trim_input_loss over translations x the 24 distinct rotations of the 4x4x4 Euler lattice (the
+    stanford.ini start grid), on the loss_small scene: the multi-group case of the structured-grid kernel."""
+    from piccolo_b200 import synth, utils as pu
+    small = np.load(os.path.join(HERE, "loss_small.npz"))
+    xyz, rgb, img = small["xyz"], synth.rgb_from_u8(small["rgb8"]), synth.img_from_u8(small["img8"])
+    rot = pu.generate_rot_points({"yaw_only": False, "num_yaw": 4, "num_pitch": 4, "num_roll": 4})        # deterministic order
+    rng = np.random.default_rng(21)
+    lo, hi = xyz.min(0), xyz.max(0)
+    trans = torch.from_numpy((lo + (hi - lo) * rng.uniform(0.2, 0.8, (5, 3))).astype(np.float32))
+    xyz_t, rgb_t, img_t = torch.from_numpy(xyz), torch.from_numpy(rgb), torch.from_numpy(img)
+    tt, rr = ref_utils.trim_input_loss(img_t, xyz_t, rgb_t, trans, rot, 10)
+    grid = torch.cat([trans.repeat_interleave(len(rot), 0), rot.repeat(len(trans), 1)], 1).numpy()
+    table = np.array([ref_loss_grad(ref_omniloc, xyz, rgb, img, g, torch.float32)[0] for g in grid])
+    np.savez_compressed(os.path.join(HERE, "score_lattice.npz"), trans=trans.numpy(), rot=rot.numpy(), loss_table=table,
+                        top10_trans=tt.numpy(), top10_rot=rr.numpy())
+    print("score_lattice: best", table.min(), "worst", table.max(), "poses", len(table))
+
+
 def main():
+    if "lattice" in sys.argv[1:]:                 # only the newest fixture (the others take minutes)
+        ref_omniloc, ref_utils = import_reference()
+        make_score_lattice(ref_omniloc, ref_utils)
+        return
     from piccolo_b200 import synth
     ref_omniloc, ref_utils = import_reference()
     torch.manual_seed(2)

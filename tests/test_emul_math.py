@@ -124,3 +124,31 @@ def test_emulated_structured_grid_on_the_euler_lattice(golden):
             want = orc.loss_and_grad_np(xyz, rgb, img, np.concatenate([t, rot[j]]).astype(np.float64), np.float64, want_grad=False)[0]
             worst = max(worst, abs(loss[k] - want) / want)
     assert worst < 1e-4, worst
+
+
+def test_emulated_structured_grid_reproduces_reference_lattice_table(golden):
+    """tests/golden/score_lattice.npz: trim_input_loss of the UNMODIFIED reference over 5 translations x the 24 lattice
+    rotations.  The structured evaluation (6 groups of 4, numpy mirror of the plan kernel + host emulation of
+    pcl_grid_base / pcl_grid_member) reproduces the reference's loss table to the 1e-4 gate and its top-10 order."""
+    from oracle import piccolo_oracle as orc
+    g, small = golden("score_lattice"), golden("loss_small")
+    rgb, img = synth.rgb_from_u8(small["rgb8"]), synth.img_from_u8(small["img8"])
+    xyz = np.ascontiguousarray(small["xyz"], dtype=np.float32)
+    trans, rot = g["trans"], g["rot"]
+    groups = _group_rotations(rot)
+    assert sorted(len(m) for _, m, _ in groups) == [4] * 6
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", SRC, "-o", SO])
+    lib = ctypes.CDLL(SO)
+    fp = ctypes.POINTER(ctypes.c_float)
+    table = np.zeros(len(trans) * len(rot), np.float32)
+    for i, t in enumerate(trans):
+        for b, members, delta in groups:
+            base = np.concatenate([t, rot[b]]).astype(np.float32)
+            loss, cnt = np.zeros(len(members), np.float32), np.zeros(len(members), np.float32)
+            lib.emul_grid(xyz.ctypes.data_as(fp), rgb.ctypes.data_as(fp), ctypes.c_long(len(xyz)), img.ctypes.data_as(fp), img.shape[0], img.shape[1],
+                          base.ctypes.data_as(fp), delta.ctypes.data_as(fp), len(members), loss.ctypes.data_as(fp), cnt.ctypes.data_as(fp))
+            table[i * len(rot) + np.asarray(members)] = loss
+    np.testing.assert_allclose(table, g["loss_table"], rtol=1e-4)
+    idx = orc.topk_ascending(table, 10)
+    np.testing.assert_array_equal(trans[idx // len(rot)], g["top10_trans"])
+    np.testing.assert_array_equal(rot[idx % len(rot)], g["top10_rot"])
