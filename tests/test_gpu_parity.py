@@ -135,29 +135,6 @@ def test_grid_scoring_and_topk_match_trim_input_loss(small, golden):
     np.testing.assert_array_equal(rr.cpu().numpy(), g["all_rot"])
 
 
-def test_lattice_grid_scoring_matches_reference_trim_input_loss(small, golden):
-    """tests/golden/score_lattice.npz: the reference's trim_input_loss over 5 translations x the 24 rotations of the
-    4x4x4 Euler lattice (6 rotation groups of 4 in pcl_score_grid): loss table to 1e-4, identical top-10."""
-    from piccolo_b200 import utils as pu
-    g = golden("score_lattice")
-    img, xyz, rgb = cu(small["img"]), cu(small["xyz"]), cu(small["rgb"])
-    trans, rot = cu(g["trans"]), cu(g["rot"])
-    table = pu.score_grid(img, xyz, rgb, trans, rot).cpu().numpy().reshape(-1)
-    # 1e-4 everywhere; a single point within ~1e-7 rad of the panorama seam / a black-texel edge may fall on the other side of
-    # that discontinuity than in the reference's fp32 run and move one entry of this 4 k-point fixture by up to 0.5/M
-    ref_table = g["loss_table"]
-    flip = 0.5 / 4000.0
-    within = np.abs(table - ref_table) <= LOSS_RTOL * ref_table
-    assert within.mean() >= 0.98 and (np.abs(table - ref_table) <= LOSS_RTOL * ref_table + flip).all(), np.abs(table / ref_table - 1).max()
-    tt, rr = pu.trim_input_loss(img, xyz, rgb, trans, rot, 10)
-    ours = {tuple(np.round(np.concatenate([a, b]), 5)) for a, b in zip(tt.cpu().numpy(), rr.cpu().numpy())}
-    theirs = {tuple(np.round(np.concatenate([a, b]), 5)) for a, b in zip(g["top10_trans"], g["top10_rot"])}
-    assert len(ours & theirs) >= 9
-    if within.all():                                                   # no flip: the order is the reference's too
-        np.testing.assert_array_equal(tt.cpu().numpy(), g["top10_trans"])
-        np.testing.assert_array_equal(rr.cpu().numpy(), g["top10_rot"])
-
-
 def _rot_lists():
     from piccolo_b200 import utils as pu
     rng = np.random.default_rng(11)
