@@ -263,7 +263,7 @@ extern "C" int pcl_score_grid(const pcl_cloud* c, const pcl_image* im, const flo
   }
   const int TB = PCL_MAX_POSE_BLOCK / r;                  // translations per CTA: TB·R <= 32 poses
   const int gy = (int)((t + TB - 1) / TB);
-  const long long n_rows = c->n_pad / PCL_THREADS;
+  const long long n_rows = (c->n + PCL_THREADS - 1) / PCL_THREADS;      // rows with real points only (see pcl_plan)
   const int resident = pcl_grid_sms() * 3;
   long long gx = 1;
   double best = -1.0;

@@ -446,7 +446,9 @@ static int pcl_num_sms() {
 static PclLaunchPlan pcl_plan(const pcl_cloud* c, int64_t P, bool bwd) {
   PclLaunchPlan pl;
   pl.NS = bwd ? PCL_NSUM : 2;
-  pl.n_rows = c->n_pad / PCL_THREADS;
+  // rows that hold real points (the arrays are padded further, to PCL_TILE_ALIGN): padding rows are never scheduled —
+  // they used to land on the last CTA's single-row path and made it the straggler every launch waits for
+  pl.n_rows = (c->n + PCL_THREADS - 1) / PCL_THREADS;
   const int resident = pcl_num_sms() * (bwd ? 2 : 3);
   // pose block: as many poses per CTA as possible (point loads amortise over the block) while leaving
   // enough CTAs to fill the machine
