@@ -71,7 +71,26 @@ def make_score_lattice(ref_omniloc, ref_utils):
     print("score_lattice: best", table.min(), "worst", table.max(), "poses", len(table))
 
 
+def make_color_small():
+    """fixture: colour preprocessing (color_utils.py:7-65 color_mod, :146-234 color_match) of the unmodified reference on
+    a perturbed 64x128 panorama (gamma, white balance, re-textured patches) against a 20 k-point cloud."""
+    from piccolo_b200 import synth
+    sys.path.insert(0, REF)
+    import color_utils as ref_color
+    sc = synth.make_scene(20000, 64, 128, seed=9)
+    img8 = synth.perturb_panorama(sc.img8, seed=4, gamma=1.15, wb=(1.0, 0.95, 1.04), retexture_frac=0.1)
+    img, rgb = torch.from_numpy(synth.img_from_u8(img8)), torch.from_numpy(synth.rgb_from_u8(sc.rgb8))
+    mod_img, mod_rgb = ref_color.color_mod(img.clone(), rgb.clone(), 256)
+    match_img = ref_color.color_match(img.clone(), rgb.clone())
+    np.savez_compressed(os.path.join(HERE, "color_small.npz"), img8=img8, rgb8=sc.rgb8, mod_img=mod_img.numpy(), mod_rgb=mod_rgb.numpy(),
+                        match_img=match_img.numpy())
+    print("color_small: lit fraction", float((img8.reshape(-1, 3).sum(1) > 0).mean()), "match range", float(match_img.min()), float(match_img.max()))
+
+
 def main():
+    if "color" in sys.argv[1:]:
+        make_color_small()
+        return
     if "lattice" in sys.argv[1:]:                 # only the newest fixture (the others take minutes)
         ref_omniloc, ref_utils = import_reference()
         make_score_lattice(ref_omniloc, ref_utils)
@@ -235,6 +254,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "loss_medium.npz"), poses=poses2, loss32=np.array(l32), grad32=np.array(g32),
                         loss64=np.array(l64), grad64=np.array(g64))
     print("loss_medium", l32)
+    make_score_lattice(ref_omniloc, ref_utils)
+    make_color_small()
 
 
 if __name__ == "__main__":
