@@ -34,13 +34,14 @@
 #ifndef PICCOLO_B200_H
 #define PICCOLO_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define PCL_ABI_VERSION 1
+#define PCL_ABI_VERSION 2
 
 typedef enum pcl_status {
   PCL_OK = 0,
@@ -64,11 +65,19 @@ typedef enum pcl_status {
 typedef struct pcl_cloud pcl_cloud;
 typedef struct pcl_image pcl_image;
 typedef struct pcl_refine pcl_refine;
+typedef struct pcl_comm pcl_comm;
 
 int pcl_abi_version(void);
 const char* pcl_last_error(void);
 /* number of kernels launched by this library in the calling process (all threads) since load */
 int64_t pcl_launch_count(void);
+
+/* Tuning knobs for A/B measurements and tests (process-global; defaults are read once from PCL_<NAME> in the
+ * environment; value < 0 restores the default): PERSIST (1: small refinement batches run all iterations in one
+ * cooperative launch), PDL (programmatic dependent launch of per-iteration launches), PB_FWD / PB_BWD (poses per
+ * CTA of the generic kernels, 0 = auto), WAVES, SWAP, GRID_SWAP (block order), SMALL_TABLE (compact texel table for
+ * small gradient batches), RF_NPB (candidates per pose block of the fused refinement, 0 = auto). */
+int pcl_set_option(const char* name, int value);
 
 /* ---- coloured point cloud ------------------------------------------------------------------ */
 /* xyz_n3_dev, rgb_n3_dev: (N,3) float32.  q: out_of_room_quantile (clamp box = order statistics
@@ -144,15 +153,44 @@ int pcl_refine_create(int b, double lr, double factor, int patience, int batch_s
 /* load B start poses and reset Adam / plateau state */
 int pcl_refine_reset(pcl_refine* r, const float* poses_b6_dev, void* stream);
 /* run num_iter iterations: each is ONE kernel = loss + backward + reduction + Adam + plateau + clamp; batches of <= 16
- * candidates run ALL iterations in one cooperative launch (cudaLaunchCooperativeKernel: one grid barrier per iteration),
- * with the per-iteration launches as fallback where the device refuses it (PCL_PERSIST=0 forces the fallback) */
+ * candidates run ALL iterations in one cooperative launch (cudaLaunchCooperativeKernel; pose blocks alternate so that
+ * the per-iteration grid barrier of one block is hidden behind the other block's work), with per-iteration launches of
+ * the same arithmetic (bit-identical trajectories) where the device refuses it (option PERSIST=0 forces them) */
 int pcl_refine_run(pcl_refine* r, const pcl_cloud* c, const pcl_image* im, int num_iter, void* stream);
+/* The same run with the POINTS of the cloud sharded over the ranks of `comm` (the B < #GPUs case: 6 candidates
+ * cannot fill 8 GPUs by candidate sharding): every rank holds the same cloud, image and refiner state and evaluates
+ * points [N*rank/nranks, N*(rank+1)/nranks); the per-CTA partial sums (14 scalars per candidate) travel as peer stores
+ * over NVLink inside the persistent kernel, every rank reduces all records in the same order and steps the optimiser
+ * itself, so the states stay bit-identical on all ranks with no host round-trip and no collective library call.
+ * All ranks must call with the same B, num_iter and cloud size.  B <= 16. */
+int pcl_refine_run_sharded(pcl_refine* r, const pcl_cloud* c, const pcl_image* im, int num_iter, pcl_comm* comm, void* stream);
 /* pose_b6_dev: what the reference returns (clamped parameter, or the un-clamped copy under batch
  * semantics); param_b6_dev (nullable): Adam's clamped parameter; loss_b_dev: loss of the LAST forward;
  * lr_b_dev (nullable, double): current learning rates */
 int pcl_refine_read(const pcl_refine* r, float* pose_b6_dev, float* param_b6_dev, float* loss_b_dev,
                     double* lr_b_dev, void* stream);
 void pcl_refine_destroy(pcl_refine* r);
+
+/* ---- peer-memory communicator of the ranks of one box (one process per GPU) ---------------------------------- */
+/* The reference is single-device (localize.py:124); SURVEY 8b/8e ask for the sharding glue in the ABI so that a caller
+ * without torch.distributed can shard.  Every rank creates a window (cudaMalloc, zero-filled; window_bytes 0 = 16 MB),
+ * the 64-byte CUDA IPC handles are exchanged through any host channel, pcl_comm_connect maps the peers' windows, and
+ * from then on kernels exchange data by stores and system-scope atomics over NVLink.  All ranks must issue the same
+ * sequence of collective calls (barrier, allgather, sharded refinement). */
+#define PCL_COMM_HANDLE_BYTES 64
+int pcl_comm_create(int rank, int nranks, size_t window_bytes, pcl_comm** out);
+int pcl_comm_handle(const pcl_comm* c, void* handle64);
+int pcl_comm_connect(pcl_comm* c, const void* handles_nranks_x_64);
+/* alternative: peer windows mapped by the caller (e.g. torch symmetric memory), zero-filled, >= window_bytes each */
+int pcl_comm_connect_ptrs(pcl_comm* c, void* const* windows);
+int pcl_comm_rank(const pcl_comm* c);
+int pcl_comm_size(const pcl_comm* c);
+/* stream-ordered barrier: work enqueued after it on `stream` starts when every rank's earlier work has finished */
+int pcl_comm_barrier(pcl_comm* c, void* stream);
+/* dst_dev[k*n + i] = src_dev[i] of rank k, n <= 16384 floats per rank — the all-gather of per-pose losses after sharded
+ * scoring and of the (loss, pose) rows before the arg-min */
+int pcl_comm_allgather_f32(pcl_comm* c, const float* src_dev, int n, float* dst_dev, void* stream);
+void pcl_comm_destroy(pcl_comm* c);
 
 #ifdef __cplusplus
 }

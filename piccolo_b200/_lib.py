@@ -40,7 +40,18 @@ SIGNATURES = {
     "pcl_refine_reset": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "pcl_refine_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "pcl_refine_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pcl_refine_run_sharded": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "pcl_refine_destroy": (None, [ctypes.c_void_p]),
+    "pcl_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
+    "pcl_comm_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, c_void_pp]),
+    "pcl_comm_handle": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "pcl_comm_connect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "pcl_comm_connect_ptrs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "pcl_comm_rank": (ctypes.c_int, [ctypes.c_void_p]),
+    "pcl_comm_size": (ctypes.c_int, [ctypes.c_void_p]),
+    "pcl_comm_barrier": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "pcl_comm_allgather_f32": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "pcl_comm_destroy": (None, [ctypes.c_void_p]),
 }
 
 _lib = None
@@ -64,7 +75,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.pcl_abi_version() != 1:
+    if lib.pcl_abi_version() != 2:
         raise PiccoloError("libpiccolo_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -74,6 +85,11 @@ def check(rc: int) -> None:
     if rc != 0:
         msg = load().pcl_last_error()
         raise PiccoloError(f"piccolo_b200 call failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def set_option(name: str, value: int) -> None:
+    """Tuning knob of the library (include/piccolo_b200.h: pcl_set_option); value < 0 restores the default."""
+    check(load().pcl_set_option(name.encode(), int(value)))
 
 
 def launch_count() -> int:

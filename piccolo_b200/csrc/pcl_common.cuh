@@ -20,6 +20,11 @@ void pcl_set_error(const char* fmt, ...);
 cudaError_t pcl_pool_alloc(void** p, size_t bytes, cudaStream_t st);
 void pcl_pool_free(void* p, cudaStream_t st);
 extern std::atomic<long long> g_pcl_launches;
+int pcl_num_sms();
+// process-global tuning knobs (pcl_set_option / PCL_<NAME> in the environment, read once)
+enum { PCL_OPT_PERSIST = 0, PCL_OPT_PDL, PCL_OPT_PB_FWD, PCL_OPT_PB_BWD, PCL_OPT_WAVES, PCL_OPT_SWAP, PCL_OPT_GRID_SWAP, PCL_OPT_SMALL_TABLE,
+       PCL_OPT_RF_NPB, PCL_OPT_COUNT };
+int pcl_opt(int id);
 
 #define PCL_CUDA(expr)                                                                         \
   do {                                                                                         \
@@ -73,18 +78,45 @@ struct PclRefineState {
 
 struct pcl_refine {
   cudaStream_t owner;
-  char* block;                  // one allocation: state | evalp | loss | counters
+  char* block;                  // one allocation: state | evalp | loss | counters | arrive | tickets
   int B, patience, batch_semantics;
   long long steps_done;         // Adam step count so far (identical for all candidates)
   double lr0, factor;
   PclRefineState* state;        // [B]
   float* evalp;                 // [B][6] pose evaluated by the next forward
+  float* loss;                  // [B]
+  // generic path (B > 16): one launch of pcl_sample_kernel per iteration
   double* partial;              // grow-only scratch for per-CTA partial sums
   size_t partial_floats;
-  unsigned int* counters;       // last-block-done tickets
-  float* loss;                  // [B]
+  unsigned int* counters;       // last-block-done tickets, [B]
+  // fused path (B <= 16): pcl_refine.cuh
+  double* rec;                  // grow-only: per-CTA records [2][nblk][G][32]
+  size_t rec_doubles;
+  unsigned int* arrive;         // [PCL_RF_MAXBLK] monotonic arrival counters of the split-phase barrier
+  unsigned int arrive_base[8];  // their current values (host copy; a run advances the counters of ITS pose blocks only)
+  unsigned int* ready;          // [PCL_RF_MAXBLK] monotonic "poses published" flags of the service CTA
+  unsigned int ready_base[8];
+  float* posebuf;               // [min(B,16)][12] published poses
+  unsigned int* tickets;        // [PCL_RF_MAXBLK] last-block-done tickets of the per-iteration fallback
   double* bc_dev;               // grow-only: per-iteration Adam bias corrections of a persistent run, [num_iter][2]
   size_t bc_cap;
+};
+
+// Peer-memory window of one rank (pcl_comm.cu): cudaMalloc'ed, IPC-mapped into every other rank of the box.
+// Layout: [0) barrier counter | [64) refinement arrival counters | [128) all-gather counter | [1024) all-gather
+// slots [2][nranks][PCL_COMM_AG_MAX] floats | [rec_off) refinement records.
+#define PCL_COMM_OFF_BAR 0
+#define PCL_COMM_OFF_ARRIVE 64
+#define PCL_COMM_OFF_AG 128
+#define PCL_COMM_OFF_AGDATA 1024
+#define PCL_COMM_AG_MAX 16384
+#define PCL_COMM_MAXRANKS 8
+struct pcl_comm {
+  int rank, nranks, connected, device;
+  size_t bytes, rec_off, rec_bytes;
+  char* peer[PCL_COMM_MAXRANKS];        // peer[rank] is the local window
+  unsigned int bar_epoch, ag_epoch;     // host copies of the monotonic counters (identical call sequences on all ranks)
+  unsigned int arrive_base[8];
 };
 
 struct PclCloudView {

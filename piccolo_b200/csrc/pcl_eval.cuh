@@ -319,6 +319,7 @@ PCL_HD void pcl_eval(const PclPose& P, const PclImage& I, float px, float py, fl
   pcl_fetch_basis<FMT>(I, idx, tx - PCL_MAGIC_F, ty - PCL_MAGIC_F, b);
 
   float d[3], dsdx[3], dsdy[3], ssum = -0.0f;   // -0.0f + x == x exactly: the first add folds away
+  bool all_zero = true;
   const float col[3] = {cr, cg, cb};
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -326,13 +327,16 @@ PCL_HD void pcl_eval(const PclPose& P, const PclImage& I, float px, float py, fl
     const float dyv = fmaf(fx, b.ddx[c], b.dy0[c]);        // bottom - top
     const float s = fmaf(fy, dyv, top);
     ssum += s;
+    if (FMT == PCL_FMT_F32) all_zero = all_zero && (s == 0.0f);
     d[c] = fmaf(s, I.tex_scale, -col[c]);
     if (BWD) {
       dsdx[c] = fmaf(fy, b.ddx[c], b.dxt[c]);
       dsdy[c] = dyv;
     }
   }
-  const bool m = valid && (ssum > 0.0f);      // texels are >= 0, so Σ == 0  <=>  all three are 0
+  // zero mask (omniloc.py:198: all three channels == 0).  The u8 tables hold texels >= 0, where Σ == 0 <=> all
+  // three are 0 (one compare); fp32 tables take arbitrary floats, negative ones included: channel-wise test
+  const bool m = valid && (FMT == PCL_FMT_F32 ? !all_zero : (ssum > 0.0f));
   const float e2 = fmaf(d[2], d[2], fmaf(d[1], d[1], d[0] * d[0]));
   float einv = 0.0f, e;
   if (BWD) { einv = pcl_rsqrt(fmaxf(e2, 1e-37f)); e = e2 * einv; } else { e = pcl_sqrt(e2); }
@@ -425,6 +429,7 @@ PCL_HD void pcl_grid_member(const PclImage& I, const PclGridBase& b, float delta
   PclBasis bs;
   pcl_fetch_basis<FMT>(I, b.yrow + xi, x0f, b.y0f, bs);
   float d[3], ssum = -0.0f;
+  bool all_zero = true;
   const float col[3] = {cr, cg, cb};
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -432,9 +437,10 @@ PCL_HD void pcl_grid_member(const PclImage& I, const PclGridBase& b, float delta
     const float dyv = fmaf(fx, bs.ddx[c], bs.dy0[c]);
     const float s = fmaf(b.fy, dyv, top);
     ssum += s;
+    if (FMT == PCL_FMT_F32) all_zero = all_zero && (s == 0.0f);
     d[c] = fmaf(s, I.tex_scale, -col[c]);
   }
-  const bool m = valid && (ssum > 0.0f);
+  const bool m = valid && (FMT == PCL_FMT_F32 ? !all_zero : (ssum > 0.0f));
   const float e = pcl_sqrt(fmaf(d[2], d[2], fmaf(d[1], d[1], d[0] * d[0])));
   se += m ? e : 0.0f;
   sm += m ? 1.0f : 0.0f;

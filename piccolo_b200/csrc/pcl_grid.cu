@@ -225,15 +225,6 @@ __global__ void pcl_grid_expand_kernel(const float* __restrict__ trans, const fl
   for (int k = 0; k < 3; ++k) { poses6[6 * p + k] = trans[3 * i + k]; poses6[6 * p + 3 + k] = rot[3 * j + k]; }
 }
 
-static int pcl_grid_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-  }
-  return sms;
-}
-
 template <int FMT>
 static cudaError_t pcl_grid_launch_fmt(dim3 grid, cudaStream_t st, const PclCloudView& C, const PclImage& I, const float* trans, int T,
                                        int TB, const PclGridPlan* plan, long long n_rows, double* partial, unsigned int* counters,
@@ -264,7 +255,7 @@ extern "C" int pcl_score_grid(const pcl_cloud* c, const pcl_image* im, const flo
   const int TB = PCL_MAX_POSE_BLOCK / r;                  // translations per CTA: TB·R <= 32 poses
   const int gy = (int)((t + TB - 1) / TB);
   const long long n_rows = (c->n + PCL_THREADS - 1) / PCL_THREADS;      // rows with real points only (see pcl_plan)
-  const int resident = pcl_grid_sms() * 3;
+  const int resident = pcl_num_sms() * 3;
   long long gx = 1;
   double best = -1.0;
   for (int w = 1; w <= 4; ++w) {                          // 1..4 whole resident waves, the best-filled one
@@ -291,8 +282,7 @@ extern "C" int pcl_score_grid(const pcl_cloud* c, const pcl_image* im, const flo
   if (e == cudaSuccess) {
     PclCloudView C = {c->x, c->y, c->z, c->r, c->g, c->b, (long long)c->n};
     const PclImage& I = im->view;
-    const char* sw = getenv("PCL_GRID_SWAP");
-    const int swap = (sw ? atoi(sw) : 1) && gx <= 65535;
+    const int swap = pcl_opt(PCL_OPT_GRID_SWAP) && gx <= 65535;
     const dim3 grid = swap ? dim3((unsigned int)gy, (unsigned int)gx) : dim3((unsigned int)gx, (unsigned int)gy);
     switch (I.fmt) {
       case PCL_FMT_U8Q: e = pcl_grid_launch_fmt<PCL_FMT_U8Q>(grid, st, C, I, trans_t3_dev, (int)t, TB, plan, n_rows, partial, counters, loss_tr_dev, count_tr_dev, swap); break;

@@ -1,0 +1,474 @@
+// Fused refinement of small candidate batches (B <= 16): device code shared by the persistent kernel and the
+// per-iteration fallback kernel (pcl_refine.cu instantiates both per texel format).
+//
+// Replaces the optimisation loops of the reference: omniloc.py:44-58 (`omniloc`) and :249-269 (`omniloc_batch`) =
+// per iteration { SamplingLoss / BatchSamplingLoss forward (omniloc.py:171-202, :311-356), autograd backward,
+// Adam.step, ReduceLROnPlateau.step, clamp of the translation into the quantile box }.
+//
+// Decomposition (B200, 148 SMs x 2 resident CTAs of 256 threads, 128 registers):
+//   * the cloud (or this rank's shard of it) is cut into G = 2·SMs - 1 contiguous point ranges balanced TO THE POINT,
+//     one per compute CTA; a CTA keeps its range for the whole run.
+//   * the candidates are cut into `nblk` pose blocks of <= 4 candidates.  A *phase* = one pose block over the CTA's
+//     range: groups of 4 x 256 points held in registers are evaluated against the block's poses with the 8 sums per
+//     pose accumulated in REGISTERS; the sub-1024-point remainder is spread over (pose, point) pairs, thread t taking
+//     pose t % np, so that every thread of the grid ends up within one evaluation of the mean.  One warp butterfly
+//     + fp64 shared-memory add per pose per phase (or per 32 evaluations on large clouds), one 64-byte record per
+//     pose per CTA per phase to global memory (and, when the cloud is sharded over ranks, to every peer over NVLink).
+//   * ONE SERVICE CTA (the last CTA of the grid, no points) owns the optimiser: for every (iteration, block) it waits
+//     until all records have arrived, reduces them in a fixed two-level fp64 order, steps Adam / plateau / clamp with
+//     one thread per (candidate, parameter), and publishes the block's next poses behind a release flag.
+//   * split-phase hand-over: a compute CTA that has written its record of block b ARRIVES on b's counter and moves
+//     straight on to the next block; it needs b's new poses only one whole round of phases later, and one of its
+//     warps prefetches them into the spare pose buffer while the others still compute.  Nobody spins in steady
+//     state: the barrier skew, the serial optimiser step, the NVLink latency and the straggler CTA are all hidden
+//     behind the other blocks' work.  (B = 1 has nothing to hide behind and pays the chain once per iteration.)
+#pragma once
+#include "pcl_common.cuh"
+
+#define PCL_RF_MAXB 16          // candidates of a fused run
+#define PCL_RF_MAXNPB 4         // candidates per pose block (their 8 sums live in registers)
+#define PCL_RF_MAXBLK 8
+#define PCL_RF_KK 4             // points per thread per group
+#define PCL_RF_GROUP (PCL_RF_KK * PCL_THREADS)
+#define PCL_RF_FLUSH 8          // groups between two flushes of the fp32 register sums into the fp64 shared-memory row
+#define PCL_RF_MAXRANKS 8
+
+struct PclRfParams {
+  PclCloudView C;
+  PclImage I;
+  int B, nblk, npb;             // candidates, pose blocks, candidates per block (the last block may hold fewer)
+  long long p_begin, p_end;     // this rank's point range
+  int G;                        // CTAs per rank
+  int rank, nranks;
+  double* rec[PCL_RF_MAXRANKS];           // record buffers of all ranks (rec[rank] is local): [2][nblk][nranks*G][MAXNPB*8]
+  unsigned int* arrive[PCL_RF_MAXRANKS];  // arrival counters of all ranks: [nblk], monotonic
+  unsigned int arrive_base[PCL_RF_MAXBLK];   // value of block b's counter when this run starts
+  int parity0;                  // record parity of this run's first iteration (records are double-buffered by iteration parity)
+  unsigned int* ready;          // [nblk] local: ready[b] - ready_base[b] = iterations of block b whose poses are published
+  unsigned int ready_base[PCL_RF_MAXBLK];
+  float* posebuf;               // [B][12] local: PclPose of every candidate for its next phase (valid behind `ready`)
+  const double* bc;             // [num_iter][2] = {1 - 0.9^step, sqrt(1 - 0.999^step)} (host libm, as python's `beta ** step`)
+  int num_iter;
+  PclRefineState* state;        // [B] global
+  float* evalp;                 // [B][6] global
+  float* loss;                  // [B] global (nullable)
+  const float* box;             // clamp box {lo(3), hi(3)}
+  double factor;
+  int patience, batch_semantics;
+};
+
+__device__ __forceinline__ unsigned int pcl_ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int pcl_ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Warp reduction of 8 values with a halving butterfly (7 + 2 shuffles instead of 40).  On return lane L with
+// L % 4 == 0 holds the warp sum of value index pcl_rf_bfly_index(L) in v[0].
+__device__ __forceinline__ void pcl_rf_warp_reduce8(float (&v)[8], const int lane) {
+  int n = 8;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    if (n > 1) {
+      const bool up = (lane & o) != 0;
+      n >>= 1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < n) {
+          const float send = up ? v[i] : v[i + n];
+          const float keep = up ? v[i + n] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+    }
+  }
+}
+__device__ __forceinline__ int pcl_rf_bfly_index(const int lane) {
+  return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+}
+
+__device__ __forceinline__ void pcl_rf_zero(PclAcc& a) {
+  a.se = -0.f; a.sm = -0.f; a.ax = -0.f; a.ay = -0.f; a.az = -0.f; a.tx = -0.f; a.ty = -0.f; a.tz = -0.f;   // -0 + x == x
+}
+
+// fp32 register sums of one pose -> the warp's private fp64 shared-memory row
+__device__ __forceinline__ void pcl_rf_flush(PclAcc& a, double* __restrict__ row8, const int lane) {
+  float v[8] = {a.se, a.sm, a.ax, a.ay, a.az, a.tx, a.ty, a.tz};
+  pcl_rf_warp_reduce8(v, lane);
+  if ((lane & 3) == 0) row8[pcl_rf_bfly_index(lane)] += (double)v[0];
+  pcl_rf_zero(a);
+}
+
+// One phase: the CTA's points [c_begin, c_end) against the np poses of a block.  On return (after the trailing
+// __syncthreads) s_acc[w][p][0..7] hold warp w's fp64 sums {Σ m e, Σ m, a(3), τ(3)} of pose p.
+struct PclRfNoHook { __device__ __forceinline__ void operator()() const {} };
+
+// `hook` runs once, after the full groups and before the remainder (the persistent kernel prefetches the next phase's
+// poses there with one warp).
+template <int FMT, int NPB, typename Hook>
+__device__ __forceinline__ void pcl_rf_phase(const PclCloudView& C, const PclImage& I, const PclPose* __restrict__ s_pose, const int np,
+                                             const long long c_begin, const long long c_end, double (*s_acc)[NPB][PCL_NSUM],
+                                             const int tid, const int lane, const int warp, const Hook& hook) {
+  // each warp owns its rows of s_acc: no CTA-wide synchronisation until the end of the phase
+  for (int i = lane; i < NPB * PCL_NSUM; i += 32) (&s_acc[warp][0][0])[i] = 0.0;
+  __syncwarp();
+
+  PclAcc acc[NPB];
+#pragma unroll
+  for (int p = 0; p < NPB; ++p) pcl_rf_zero(acc[p]);
+
+  const long long n_groups = (c_end - c_begin) / PCL_RF_GROUP;
+  long long i0 = c_begin + tid;
+  int pending = 0;
+  for (long long g = 0; g < n_groups; ++g, i0 += PCL_RF_GROUP) {
+    float px[PCL_RF_KK], py[PCL_RF_KK], pz[PCL_RF_KK], cr[PCL_RF_KK], cg[PCL_RF_KK], cb[PCL_RF_KK];
+#pragma unroll
+    for (int j = 0; j < PCL_RF_KK; ++j) {
+      const long long i = i0 + (long long)j * PCL_THREADS;
+      px[j] = __ldg(C.x + i); py[j] = __ldg(C.y + i); pz[j] = __ldg(C.z + i);
+      cr[j] = __ldg(C.r + i); cg[j] = __ldg(C.g + i); cb[j] = __ldg(C.b + i);
+    }
+#pragma unroll
+    for (int p = 0; p < NPB; ++p) {
+      if (p < np) {
+        const PclPose pose = s_pose[p];
+#pragma unroll
+        for (int j = 0; j < PCL_RF_KK; ++j) pcl_eval<FMT, true>(pose, I, px[j], py[j], pz[j], cr[j], cg[j], cb[j], true, acc[p]);
+      }
+    }
+    if (++pending == PCL_RF_FLUSH) {
+      pending = 0;
+#pragma unroll
+      for (int p = 0; p < NPB; ++p)
+        if (p < np) pcl_rf_flush(acc[p], s_acc[warp][p], lane);
+    }
+  }
+
+  hook();
+
+  // remainder (< 1024 points): thread t takes pose t % np and every S-th point from slot t / np, S = 256 / np
+  const long long rem0 = c_begin + n_groups * PCL_RF_GROUP;
+  const int r = (int)(c_end - rem0);
+  if (r > 0) {
+    const int S = PCL_THREADS / np;
+    const int p_t = tid % np, slot = tid / np;
+    PclAcc ar;
+    pcl_rf_zero(ar);
+    if (slot < S) {
+      const PclPose pose = s_pose[p_t];
+      for (int m0 = slot; m0 < r; m0 += PCL_RF_KK * S) {
+        float px[PCL_RF_KK], py[PCL_RF_KK], pz[PCL_RF_KK], cr[PCL_RF_KK], cg[PCL_RF_KK], cb[PCL_RF_KK];
+        bool ok[PCL_RF_KK];
+#pragma unroll
+        for (int j = 0; j < PCL_RF_KK; ++j) {
+          const int m = m0 + j * S;
+          ok[j] = m < r;
+          const long long i = rem0 + (ok[j] ? m : slot);      // masked slots re-read a valid point and are discarded
+          px[j] = __ldg(C.x + i); py[j] = __ldg(C.y + i); pz[j] = __ldg(C.z + i);
+          cr[j] = __ldg(C.r + i); cg[j] = __ldg(C.g + i); cb[j] = __ldg(C.b + i);
+        }
+#pragma unroll
+        for (int j = 0; j < PCL_RF_KK; ++j) pcl_eval<FMT, true>(pose, I, px[j], py[j], pz[j], cr[j], cg[j], cb[j], ok[j], ar);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < NPB; ++p) {
+      const bool mine = (p == p_t);
+      acc[p].se += mine ? ar.se : 0.f; acc[p].sm += mine ? ar.sm : 0.f;
+      acc[p].ax += mine ? ar.ax : 0.f; acc[p].ay += mine ? ar.ay : 0.f; acc[p].az += mine ? ar.az : 0.f;
+      acc[p].tx += mine ? ar.tx : 0.f; acc[p].ty += mine ? ar.ty : 0.f; acc[p].tz += mine ? ar.tz : 0.f;
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < NPB; ++p)
+    if (p < np) pcl_rf_flush(acc[p], s_acc[warp][p], lane);
+  __syncthreads();
+}
+
+// the CTA's record of a phase: rec8[p*8 + s] = Σ_warps s_acc[w][p][s]   (threads < np*8)
+template <int NPB>
+__device__ __forceinline__ double pcl_rf_cta_sum(double (*s_acc)[NPB][PCL_NSUM], const int tid) {
+  const int p = tid >> 3, s = tid & 7;
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < PCL_WARPS; ++w) t += s_acc[w][p][s];
+  return t;
+}
+
+struct PclRfConsts {
+  const float* box;
+  double factor;
+  int patience, batch_semantics;
+};
+
+// Every thread of the CTA: deterministic two-level fp64 reduction of the block's n_rec records (slot stride
+// MAXNPB*8 doubles), then one thread per (candidate, parameter): loss + analytic gradient + torch.optim.Adam
+// (single-tensor path, betas 0.9/0.999, eps 1e-8; fp32 tensors, fp64 python scalars) + ReduceLROnPlateau(mode=min,
+// threshold 1e-4 rel, cooldown 0, min_lr 0, eps 1e-8) + translation clamp, exactly the split torch has
+// (omniloc.py:33,37,49-58).  st/evalp/pose are the block's np entries (shared or global memory).
+// Contains __syncthreads: call from all threads.  On return evalp/pose hold the next iteration's pose.
+__device__ __forceinline__ void pcl_rf_finalize(const double* __restrict__ rec, const int n_rec, const int np, double2* __restrict__ s_sum,
+                                                PclRefineState* __restrict__ st, float* __restrict__ evalp, PclPose* __restrict__ pose,
+                                                const PclImage& I, const PclRfConsts& k, const double bc1, const double bc2_sqrt, const int tid) {
+  const int nitems = np * (PCL_NSUM / 2);                        // 16-byte pairs of sums
+  const int GG = PCL_THREADS / nitems;
+  {
+    const int item = tid % nitems, g = tid / nitems;
+    double2 t = make_double2(0.0, 0.0);
+    if (g < GG) {
+      const double2* src = reinterpret_cast<const double2*>(rec) + item;
+      constexpr int stride = PCL_RF_MAXNPB * PCL_NSUM / 2;
+#pragma unroll 8
+      for (int s = g; s < n_rec; s += GG) {
+        const double2 v = __ldcg(src + (size_t)s * stride);
+        t.x += v.x; t.y += v.y;
+      }
+    }
+    s_sum[tid] = t;
+  }
+  __syncthreads();
+  double2 tot = make_double2(0.0, 0.0);
+  if (tid < nitems) {
+    for (int g = 0; g < GG; ++g) { const double2 v = s_sum[g * nitems + tid]; tot.x += v.x; tot.y += v.y; }
+  }
+  __syncthreads();
+  if (tid < nitems) s_sum[tid] = tot;
+  __syncthreads();
+  if (tid < 32) {
+    const int p = tid / 6, i = tid - 6 * p;
+    const bool act = tid < np * 6;
+    const unsigned int mask = __ballot_sync(0xffffffffu, act);
+    if (act) {
+      double sums[PCL_NSUM];
+#pragma unroll
+      for (int h = 0; h < PCL_NSUM / 2; ++h) { const double2 t = s_sum[p * (PCL_NSUM / 2) + h]; sums[2 * h] = t.x; sums[2 * h + 1] = t.y; }
+      float p6[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) p6[j] = evalp[6 * p + j];
+      float loss, grad[6];
+      pcl_finish_gradient(p6, pose[p], I, sums, &loss, nullptr, grad);
+      float gi = grad[0];
+#pragma unroll
+      for (int j = 1; j < 6; ++j) gi = (i == j) ? grad[j] : gi;
+      PclRefineState& S = st[p];
+      // Adam: exp_avg.lerp_(grad, 1-beta1); exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2); addcdiv_(m, denom, -step_size)
+      const float step_size = (float)(S.lr / bc1);
+      const float w1 = (float)(1.0 - 0.9), b2 = 0.999f, w2 = (float)(1.0 - 0.999);
+      const float m = S.m[i] + w1 * (gi - S.m[i]);
+      const float v = S.v[i] * b2 + (w2 * gi) * gi;
+      const float denom = sqrtf(v) / (float)bc2_sqrt + 1e-8f;
+      const float newp = S.param[i] - step_size * (m / denom);
+      __syncwarp(mask);                                          // every parameter thread has read lr
+      S.m[i] = m; S.v[i] = v;
+      if (i == 0) {
+        S.last_loss = loss;
+        S.step += 1;
+        const double cur = (double)loss;                         // scheduler.step(loss)
+        if (cur < S.best * (1.0 - 1e-4)) { S.best = cur; S.bad = 0; } else { S.bad += 1; }
+        if (S.bad > k.patience) {
+          const double new_lr = fmax(S.lr * k.factor, 0.0);
+          if (S.lr - new_lr > 1e-8) S.lr = new_lr;
+          S.bad = 0;
+        }
+      }
+      // clamp the translation into the quantile box; batch semantics evaluates the pre-clamp copy next (omniloc.py:260-269)
+      float c = newp;
+      if (i < 3) c = fminf(fmaxf(c, __ldg(k.box + i)), __ldg(k.box + 3 + i));
+      S.param[i] = c;
+      evalp[6 * p + i] = k.batch_semantics ? newp : c;
+      __syncwarp(mask);
+      if (i == 0) pcl_pose_from_params(evalp + 6 * p, pose[p]);
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistent kernel: ALL iterations in one cooperative launch; CTA G (the last one) is the service CTA
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pcl_rf_spin(const unsigned int* ctr, const unsigned int target, const bool sys, const unsigned int ns) {
+  if (sys) { while ((int)(pcl_ld_acquire_sys(ctr) - target) < 0) { if (ns) __nanosleep(ns); } }
+  else { while ((int)(pcl_ld_acquire_gpu(ctr) - target) < 0) { if (ns) __nanosleep(ns); } }
+}
+
+template <int FMT, int NPB>
+__global__ void __launch_bounds__(PCL_THREADS, 2) pcl_refine_persistent_kernel(const PclRfParams ps) {
+  __shared__ __align__(16) PclPose s_pose[2][PCL_RF_MAXB];       // compute: [phase parity][NPB] used; service: [0][B]
+  __shared__ double s_acc[2][PCL_WARPS][NPB][PCL_NSUM];
+  __shared__ double2 s_sum[PCL_THREADS];
+  __shared__ PclRefineState s_state[PCL_RF_MAXB];                // service CTA only
+  __shared__ float s_evalp[PCL_RF_MAXB][6];
+  __shared__ int s_pref[2];                                      // phase whose poses sit in s_pose[parity]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cta = blockIdx.x, G = ps.G, n_rec = G * ps.nranks;
+  const size_t rec_blk = (size_t)n_rec * PCL_RF_MAXNPB * PCL_NSUM;          // doubles per block
+
+  if (cta == G) {
+    // ---------------- service CTA: reduce, step the optimiser, publish ----------------
+    const PclRfConsts k = {ps.box, ps.factor, ps.patience, ps.batch_semantics};
+    if (tid < ps.B) {
+      s_state[tid] = ps.state[tid];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) s_evalp[tid][i] = ps.evalp[6 * tid + i];
+      pcl_pose_from_params(s_evalp[tid], s_pose[0][tid]);
+    }
+    __syncthreads();
+    for (int it = 0; it < ps.num_iter; ++it) {
+      for (int b = 0; b < ps.nblk; ++b) {
+        const int p0 = b * ps.npb, np = min(ps.npb, ps.B - p0);
+        if (tid == 0) pcl_rf_spin(ps.arrive[ps.rank] + b, ps.arrive_base[b] + (unsigned int)(it + 1) * (unsigned int)n_rec, ps.nranks > 1, 32u);
+        __syncthreads();
+        // records are double-buffered by iteration parity: a fast rank's next record must not overwrite the copy a slower
+        // rank's service CTA is still reading
+        pcl_rf_finalize(ps.rec[ps.rank] + ((size_t)((ps.parity0 + it) & 1) * ps.nblk + b) * rec_blk, n_rec, np, s_sum, s_state + p0, &s_evalp[p0][0], &s_pose[0][p0], ps.I, k,
+                        __ldg(ps.bc + 2 * it), __ldg(ps.bc + 2 * it + 1), tid);
+        if (tid < np * 12) ps.posebuf[(size_t)p0 * 12 + tid] = reinterpret_cast<const float*>(&s_pose[0][p0])[tid];
+        __syncthreads();
+        if (tid == 0) {
+          __threadfence();
+          const unsigned int v = ps.ready_base[b] + (unsigned int)(it + 1);
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ps.ready + b), "r"(v) : "memory");
+        }
+      }
+    }
+    if (tid < ps.B) {                                            // the end state
+      ps.state[tid] = s_state[tid];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) ps.evalp[6 * tid + i] = s_evalp[tid][i];
+      if (ps.loss) ps.loss[tid] = s_state[tid].last_loss;
+    }
+    return;
+  }
+
+  // ---------------- compute CTAs ----------------
+  // this CTA's points: ranges of the rank's shard that differ by at most one point
+  const long long n_pts = ps.p_end - ps.p_begin;
+  const long long c_begin = ps.p_begin + n_pts * (long long)cta / G;
+  const long long c_end = ps.p_begin + n_pts * (long long)(cta + 1) / G;
+  const size_t my_slot = ((size_t)ps.rank * G + cta) * PCL_RF_MAXNPB * PCL_NSUM;
+  if (tid < 2) s_pref[tid] = -1;
+  __syncthreads();
+
+  int ph = 0;
+  for (int it = 0; it < ps.num_iter; ++it) {
+    for (int b = 0; b < ps.nblk; ++b, ++ph) {
+      const int buf = ph & 1;
+      const int p0 = b * ps.npb, np = min(ps.npb, ps.B - p0);
+      if (it == 0) {
+        if (tid < np) pcl_pose_from_params(ps.evalp + 6 * (size_t)(p0 + tid), s_pose[buf][tid]);
+        __syncthreads();
+      } else if (s_pref[buf] != ph) {                            // not prefetched (uniform: written before the last barrier)
+        if (tid == 0) pcl_rf_spin(ps.ready + b, ps.ready_base[b] + (unsigned int)it, false, 0u);
+        __syncthreads();
+        if (tid < np * 12) reinterpret_cast<float*>(&s_pose[buf][0])[tid] = __ldcg(ps.posebuf + (size_t)p0 * 12 + tid);
+        __syncthreads();
+      }
+      // the last warp tries to fetch the NEXT phase's poses while the others are still in this phase
+      const int nb = (b + 1 == ps.nblk) ? 0 : b + 1, nit = (b + 1 == ps.nblk) ? it + 1 : it;
+      auto hook = [&]() {
+        if (warp != PCL_WARPS - 1 || nit == 0 || nit >= ps.num_iter) return;
+        unsigned int ok = 0;
+        if (lane == 0) ok = ((int)(pcl_ld_acquire_gpu(ps.ready + nb) - (ps.ready_base[nb] + (unsigned int)nit)) >= 0) ? 1u : 0u;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) return;
+        const int q0 = nb * ps.npb, nq = min(ps.npb, ps.B - q0);
+        for (int i = lane; i < nq * 12; i += 32) reinterpret_cast<float*>(&s_pose[buf ^ 1][0])[i] = __ldcg(ps.posebuf + (size_t)q0 * 12 + i);
+        if (lane == 0) s_pref[buf ^ 1] = ph + 1;
+      };
+      pcl_rf_phase<FMT, NPB>(ps.C, ps.I, s_pose[buf], np, c_begin, c_end, s_acc[buf], tid, lane, warp, hook);
+      if (warp == 0) {
+        if (lane < np * PCL_NSUM) {
+          const double t = pcl_rf_cta_sum<NPB>(s_acc[buf], lane);
+          const size_t off = ((size_t)((ps.parity0 + it) & 1) * ps.nblk + b) * rec_blk + my_slot + lane;
+          for (int rk = 0; rk < ps.nranks; ++rk) ps.rec[rk][off] = t;
+        }
+        __syncwarp();
+        if (lane < ps.nranks) {
+          if (ps.nranks > 1) { __threadfence_system(); atomicAdd_system(ps.arrive[lane] + b, 1u); }
+          else { __threadfence(); atomicAdd(ps.arrive[0] + b, 1u); }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-iteration fallback (single rank): grid (G, nblk), the last CTA of a block finishes it.  Same ranges, same
+// phase arithmetic, same record order and the same finalize as the persistent kernel: bit-identical trajectories.
+// ------------------------------------------------------------------------------------------------
+template <int FMT, int NPB>
+__global__ void __launch_bounds__(PCL_THREADS, 2) pcl_refine_iter_kernel(const PclRfParams ps, unsigned int* __restrict__ tickets,
+                                                                         const double bc1, const double bc2_sqrt) {
+  __shared__ __align__(16) PclPose s_pose[PCL_RF_MAXNPB];
+  __shared__ double s_acc[PCL_WARPS][NPB][PCL_NSUM];
+  __shared__ double2 s_sum[PCL_THREADS];
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cta = blockIdx.x, b = blockIdx.y, G = ps.G;
+  const int p0 = b * ps.npb, np = min(ps.npb, ps.B - p0);
+#if __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");             // the previous iteration's poses are complete
+#endif
+  if (tid < np) pcl_pose_from_params(ps.evalp + 6 * (size_t)(p0 + tid), s_pose[tid]);
+  __syncthreads();
+  const long long n_pts = ps.p_end - ps.p_begin;
+  const long long c_begin = ps.p_begin + n_pts * (long long)cta / G;
+  const long long c_end = ps.p_begin + n_pts * (long long)(cta + 1) / G;
+  pcl_rf_phase<FMT, NPB>(ps.C, ps.I, s_pose, np, c_begin, c_end, s_acc, tid, lane, warp, PclRfNoHook());
+  double* rec = ps.rec[0] + (size_t)b * G * PCL_RF_MAXNPB * PCL_NSUM;
+  if (tid < np * PCL_NSUM) rec[(size_t)cta * PCL_RF_MAXNPB * PCL_NSUM + tid] = pcl_rf_cta_sum<NPB>(s_acc, tid);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(tickets + b, 1u) == (unsigned int)G - 1u);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const PclRfConsts k = {ps.box, ps.factor, ps.patience, ps.batch_semantics};
+  pcl_rf_finalize(rec, G, np, s_sum, ps.state + p0, ps.evalp + 6 * (size_t)p0, s_pose, ps.I, k, bc1, bc2_sqrt, tid);
+  if (tid < np && ps.loss) ps.loss[p0 + tid] = ps.state[p0 + tid].last_loss;
+  if (tid == 0) tickets[b] = 0u;                                 // self-resetting
+}
+
+// launch helpers instantiated per texel format (pcl_refine_fmt*.cu)
+template <int FMT> cudaError_t pcl_rf_launch_persistent(const PclRfParams& ps, cudaStream_t st);
+template <int FMT> cudaError_t pcl_rf_launch_iter(const PclRfParams& ps, unsigned int* tickets, double bc1, double bc2_sqrt, bool pdl, cudaStream_t st);
+
+#define PCL_RF_INSTANTIATE(FMT)                                                                                                     \
+  template <> cudaError_t pcl_rf_launch_persistent<FMT>(const PclRfParams& ps, cudaStream_t st) {                                   \
+    PclRfParams p = ps;                                                                                                             \
+    void* args[] = {&p};                                                                                                            \
+    const void* fn = ps.npb == 1 ? (const void*)pcl_refine_persistent_kernel<FMT, 1>                                                \
+                   : ps.npb == 2 ? (const void*)pcl_refine_persistent_kernel<FMT, 2>                                                \
+                   : ps.npb == 3 ? (const void*)pcl_refine_persistent_kernel<FMT, 3>                                                \
+                                 : (const void*)pcl_refine_persistent_kernel<FMT, 4>;                                               \
+    return cudaLaunchCooperativeKernel(fn, dim3(ps.G + 1), dim3(PCL_THREADS), args, 0, st);                                             \
+  }                                                                                                                                 \
+  template <> cudaError_t pcl_rf_launch_iter<FMT>(const PclRfParams& ps, unsigned int* tickets, double bc1, double bc2_sqrt, bool pdl, \
+                                                  cudaStream_t st) {                                                                \
+    cudaLaunchConfig_t cfg;                                                                                                         \
+    memset(&cfg, 0, sizeof(cfg));                                                                                                   \
+    cfg.gridDim = dim3(ps.G, ps.nblk);                                                                                              \
+    cfg.blockDim = dim3(PCL_THREADS);                                                                                               \
+    cfg.stream = st;                                                                                                                \
+    cudaLaunchAttribute attr[1];                                                                                                    \
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                                \
+    attr[0].val.programmaticStreamSerializationAllowed = 1;                                                                         \
+    cfg.attrs = attr;                                                                                                               \
+    cfg.numAttrs = pdl ? 1 : 0;                                                                                                     \
+    switch (ps.npb) {                                                                                                               \
+      case 1: return cudaLaunchKernelEx(&cfg, pcl_refine_iter_kernel<FMT, 1>, ps, tickets, bc1, bc2_sqrt);                          \
+      case 2: return cudaLaunchKernelEx(&cfg, pcl_refine_iter_kernel<FMT, 2>, ps, tickets, bc1, bc2_sqrt);                          \
+      case 3: return cudaLaunchKernelEx(&cfg, pcl_refine_iter_kernel<FMT, 3>, ps, tickets, bc1, bc2_sqrt);                          \
+      default: return cudaLaunchKernelEx(&cfg, pcl_refine_iter_kernel<FMT, 4>, ps, tickets, bc1, bc2_sqrt);                         \
+    }                                                                                                                               \
+  }

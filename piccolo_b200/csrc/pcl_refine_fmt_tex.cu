@@ -1,0 +1,5 @@
+// fused refinement kernels for texel format TEX (one translation unit per format: parallel builds)
+#include "pcl_refine.cuh"
+#include <string.h>
+
+PCL_RF_INSTANTIATE(PCL_FMT_TEX)

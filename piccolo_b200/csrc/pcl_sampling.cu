@@ -22,6 +22,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <strings.h>
+#include <mutex>
 
 // ------------------------------------------------------------------------------------------------
 // error / bookkeeping
@@ -286,152 +288,40 @@ pcl_sample_kernel(const PclCloudView C, const PclImage I, const float* poses6, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// persistent refinement: ALL iterations of a small candidate batch in one cooperative launch
-// ------------------------------------------------------------------------------------------------
-// The per-iteration launch above pays ~10 us of serial chain per iteration even on an empty cloud (fence ->
-// ticket -> last-CTA reduction -> Adam -> grid drain -> dependent launch -> pose set-up; scripts/tail_probe.py),
-// a fifth of a C2 iteration.  Here the grid (one resident wave, launched cooperatively) stays on the SMs: per
-// iteration every CTA writes its partial record, the CTAs of a pose block meet at ONE barrier, and then EVERY CTA
-// reduces the block's records and steps Adam / plateau / clamp for the block's candidates itself — redundantly, in
-// the same fixed order, so all replicas are bit-identical and the next iteration's poses are already in the CTA's
-// shared memory.  Partial records are double-buffered by iteration parity; one barrier per iteration suffices.
-struct PclPersist {
-  double* partial;              // [2][n_ranges][P][8]
-  unsigned int* barrier;        // [pose blocks] monotonic arrival counters, zero at launch
-  const double* bc;             // [num_iter][2] = {1 - 0.9^step, sqrt(1 - 0.999^step)} (host libm, as python's `beta ** step`)
-  int num_iter;
-};
-
-__device__ __forceinline__ unsigned int pcl_ld_acquire(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-template <int FMT>
-__global__ void __launch_bounds__(PCL_THREADS, 2)
-pcl_refine_persistent_kernel(const PclCloudView C, const PclImage I, const int P, const int PB, const long long n_rows,
-                             const PclFinalize fin, const PclPersist ps) {
-  constexpr int NS = PCL_NSUM;
-  constexpr int MAXB = 16;                                      // candidates per pose block (host guarantees PB <= 16)
-  __shared__ __align__(16) PclPose s_pose[PCL_MAX_POSE_BLOCK];
-  __shared__ double s_acc[PCL_WARPS][PCL_MAX_POSE_BLOCK][NS];
-  __shared__ double2 s_sum[PCL_THREADS];
-  __shared__ PclRefineState s_state[MAXB];
-  __shared__ float s_evalp[MAXB][6];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned int bp = blockIdx.y, br = blockIdx.x, n_ranges = gridDim.x;
-  const int p0 = bp * PB;
-  const int np = min(PB, P - p0);
-  if (tid < np) {
-    s_state[tid] = fin.state[p0 + tid];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) s_evalp[tid][i] = fin.evalp[6 * (size_t)(p0 + tid) + i];
-  }
-  const long long r_begin = n_rows * (long long)br / (long long)n_ranges;
-  const long long r_end = n_rows * (long long)(br + 1) / (long long)n_ranges;
-  const long long r_full = min(r_end, C.n / PCL_THREADS);
-  const int nitems = np * (NS / 2);
-  const int G = max(1, PCL_THREADS / nitems);
-
-  for (int it = 0; it < ps.num_iter; ++it) {
-    __syncthreads();                                             // s_evalp of the previous update is visible; s_acc is free
-    for (int i = tid; i < PCL_WARPS * np * NS; i += PCL_THREADS) {
-      const int w = i / (np * NS), r = i - w * (np * NS);
-      s_acc[w][r / NS][r % NS] = 0.0;
-    }
-    if (tid < np) pcl_pose_from_params(s_evalp[tid], s_pose[tid]);
-    __syncthreads();
-
-    long long r = r_begin;
-    {
-      const long long n = r_full - r, a = n >> 2, b = n & 3;
-      long long n5 = (a >= b) ? b : 0, n4 = (a >= b) ? a - b : a;
-      for (; n5 > 0; --n5, r += 5) pcl_process_rows<FMT, true, 5, NS, false>(C, I, s_pose, np, s_acc, r, tid, lane, warp);
-      for (; n4 > 0; --n4, r += 4) pcl_process_rows<FMT, true, 4, NS, false>(C, I, s_pose, np, s_acc, r, tid, lane, warp);
-    }
-    for (; r < r_full; ++r) pcl_process_rows<FMT, true, 1, NS, false>(C, I, s_pose, np, s_acc, r, tid, lane, warp);
-    for (; r < r_end; ++r) pcl_process_rows<FMT, true, 1, NS, true>(C, I, s_pose, np, s_acc, r, tid, lane, warp);
-    __syncthreads();
-
-    double* part = ps.partial + (size_t)(it & 1) * (size_t)n_ranges * (size_t)P * NS;
-    for (int i = tid; i < np * NS; i += PCL_THREADS) {
-      const int p = i / NS, s = i - p * NS;
-      double t = 0.0;
-#pragma unroll
-      for (int w = 0; w < PCL_WARPS; ++w) t += s_acc[w][p][s];
-      part[((size_t)br * (size_t)P + (size_t)(p0 + p)) * NS + s] = t;
-    }
-
-    // barrier of the pose block's CTAs (all co-resident: cooperative launch)
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      atomicAdd(ps.barrier + bp, 1u);
-      const unsigned int target = (unsigned int)(it + 1) * n_ranges;
-      while (pcl_ld_acquire(ps.barrier + bp) < target) { }
-    }
-    __syncthreads();
-
-    // every CTA: deterministic two-level reduction of the block's records (as in pcl_sample_kernel), then the update
-    {
-      const int item = tid % nitems, g = tid / nitems;
-      double2 t = make_double2(0.0, 0.0);
-      if (g < G) {
-        const double2* src = reinterpret_cast<const double2*>(part + (size_t)p0 * NS) + item;
-        const size_t stride = (size_t)P * (NS / 2);
-#pragma unroll 16
-        for (unsigned int bx = g; bx < n_ranges; bx += G) {
-          const double2 v = __ldcg(src + (size_t)bx * stride);
-          t.x += v.x; t.y += v.y;
-        }
-      }
-      s_sum[tid] = t;
-    }
-    __syncthreads();
-    double2 fin_item = make_double2(0.0, 0.0);
-    if (tid < nitems) {
-      for (int g = 0; g < G; ++g) { const double2 v = s_sum[g * nitems + tid]; fin_item.x += v.x; fin_item.y += v.y; }
-    }
-    __syncthreads();
-    if (tid < nitems) s_sum[tid] = fin_item;
-    __syncthreads();
-    if (tid < np) {
-      double sums[PCL_NSUM];
-#pragma unroll
-      for (int h = 0; h < NS / 2; ++h) {
-        const double2 t = s_sum[tid * (NS / 2) + h];
-        sums[2 * h] = t.x; sums[2 * h + 1] = t.y;
-      }
-      float loss, cnt, grad[6];
-      pcl_finish_gradient(s_evalp[tid], s_pose[tid], I, sums, &loss, &cnt, grad);
-      PclFinalize f = fin;
-      f.bc1 = __ldg(ps.bc + 2 * it); f.bc2_sqrt = __ldg(ps.bc + 2 * it + 1);
-      pcl_refine_update(s_state[tid], s_evalp[tid], grad, loss, f);
-    }
-  }
-  __syncthreads();
-  if (br == 0 && tid < np) {                                     // one replica publishes the end state
-    const int pg = p0 + tid;
-    fin.state[pg] = s_state[tid];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) fin.evalp[6 * (size_t)pg + i] = s_evalp[tid][i];
-    if (fin.loss) fin.loss[pg] = s_state[tid].last_loss;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // host-side launch
 // ------------------------------------------------------------------------------------------------
 struct PclLaunchPlan { int PB, gx, gy, NS; long long n_rows; };
 
-static int pcl_env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
+// Tuning knobs (A/B experiments and tests): process-global, read ONCE from the environment (PCL_<NAME>) on first use,
+// changed afterwards only through pcl_set_option — no getenv on the launch path.
+static const char* const g_opt_names[PCL_OPT_COUNT] = {"PERSIST", "PDL", "PB_FWD", "PB_BWD", "WAVES", "SWAP", "GRID_SWAP", "SMALL_TABLE", "RF_NPB"};
+static const int g_opt_defaults[PCL_OPT_COUNT] = {1, 1, 0, 0, 0, 1, 1, 1, 0};
+static std::atomic<int> g_opt[PCL_OPT_COUNT];
+static std::once_flag g_opt_once;
+
+static void pcl_opt_init() {
+  for (int i = 0; i < PCL_OPT_COUNT; ++i) {
+    char name[64];
+    snprintf(name, sizeof(name), "PCL_%s", g_opt_names[i]);
+    const char* v = getenv(name);
+    g_opt[i].store(v ? atoi(v) : g_opt_defaults[i]);
+  }
+}
+int pcl_opt(int id) {
+  std::call_once(g_opt_once, pcl_opt_init);
+  return g_opt[id].load(std::memory_order_relaxed);
+}
+extern "C" int pcl_set_option(const char* name, int value) {
+  std::call_once(g_opt_once, pcl_opt_init);
+  if (!name) { pcl_set_error("null option name"); return PCL_ERR_INVALID; }
+  for (int i = 0; i < PCL_OPT_COUNT; ++i) {
+    if (strcasecmp(name, g_opt_names[i]) == 0) { g_opt[i].store(value < 0 ? g_opt_defaults[i] : value); return PCL_OK; }
+  }
+  pcl_set_error("unknown option %s", name);
+  return PCL_ERR_INVALID;
 }
 
-static int pcl_num_sms() {
+int pcl_num_sms() {
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -456,14 +346,14 @@ static PclLaunchPlan pcl_plan(const pcl_cloud* c, int64_t P, bool bwd) {
   // small refinement batches: two pose blocks (twice the rows per CTA, half the row-count imbalance) measured
   // 8 % faster than one block of all candidates (B=6: 47 vs 51 us per iteration)
   if (bwd && P >= 4 && P <= 16) PB = (int)((P + 1) / 2);
-  const int pb_env = pcl_env_int(bwd ? "PCL_PB_BWD" : "PCL_PB_FWD", 0);
+  const int pb_env = pcl_opt(bwd ? PCL_OPT_PB_BWD : PCL_OPT_PB_FWD);
   if (pb_env > 0 && pb_env <= PCL_MAX_POSE_BLOCK) PB = (int)(pb_env < P ? pb_env : P);
   pl.PB = PB;
   pl.gy = (int)((P + PB - 1) / PB);
   // 1..4 full waves: take the wave count whose grid fills its slots best (CTAs do equal work)
   long long gx = 1;
   double best = -1.0;
-  const int w_env = pcl_env_int("PCL_WAVES", 0);
+  const int w_env = pcl_opt(PCL_OPT_WAVES);
   for (int w = (w_env > 0 ? w_env : 1); w <= (w_env > 0 ? w_env : 4); ++w) {
     long long g = (long long)resident * w / pl.gy;
     if (g < 1) g = 1;
@@ -480,7 +370,7 @@ static cudaError_t pcl_launch_fmt(const PclLaunchPlan& pl, const PclCloudView& C
                                   double* partial, unsigned int* counters, const PclFinalize& fin, cudaStream_t st, bool pdl) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  const int swap = (!BWD && pl.gy > 1 && pl.gx <= 65535) ? pcl_env_int("PCL_SWAP", 1) : 0;
+  const int swap = (!BWD && pl.gy > 1 && pl.gx <= 65535) ? pcl_opt(PCL_OPT_SWAP) : 0;
   cfg.gridDim = swap ? dim3(pl.gy, pl.gx) : dim3(pl.gx, pl.gy);
   cfg.blockDim = dim3(PCL_THREADS);
   cfg.stream = st;
@@ -498,7 +388,7 @@ static int pcl_launch(const PclLaunchPlan& pl, const pcl_cloud* c, const pcl_ima
   PclCloudView C = {c->x, c->y, c->z, c->r, c->g, c->b, (long long)c->n};
   cudaError_t e;
   // small forward+backward batches (refinement) read the compact companion table when the image has one
-  const PclImage& view = (BWD && P <= 16 && im->has_small && pcl_env_int("PCL_SMALL_TABLE", 1)) ? im->view_small : im->view;
+  const PclImage& view = (BWD && P <= 16 && im->has_small && pcl_opt(PCL_OPT_SMALL_TABLE)) ? im->view_small : im->view;
   switch (view.fmt) {
     case PCL_FMT_U8Q: e = pcl_launch_fmt<PCL_FMT_U8Q, BWD>(pl, C, view, poses, P, partial, counters, fin, st, pdl); break;
     case PCL_FMT_U8P: e = pcl_launch_fmt<PCL_FMT_U8P, BWD>(pl, C, view, poses, P, partial, counters, fin, st, pdl); break;
@@ -557,130 +447,17 @@ extern "C" int pcl_loss_fwd_bwd(const pcl_cloud* c, const pcl_image* im, const f
 }
 
 // ------------------------------------------------------------------------------------------------
-// C ABI: fused refinement
+// refinement of LARGE batches (B > 16; pcl_refine.cu handles the small ones): one launch per iteration for the
+// whole candidate batch, the finishing CTA of each pose block steps Adam / plateau / clamp (PCL_FIN_REFINE)
 // ------------------------------------------------------------------------------------------------
-__global__ void pcl_refine_reset_kernel(PclRefineState* st, float* evalp, const float* poses6, int B, double lr) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  PclRefineState s;
-  for (int i = 0; i < 6; ++i) { s.m[i] = 0.f; s.v[i] = 0.f; s.param[i] = poses6[6 * b + i]; evalp[6 * b + i] = poses6[6 * b + i]; }
-  s.last_loss = nanf(""); s.step = 0; s.bad = 0; s.pad = 0; s.lr = lr; s.best = INFINITY;
-  st[b] = s;
-}
-
-__global__ void pcl_refine_read_kernel(const PclRefineState* st, const float* evalp, int B, int batch, float* pose, float* param,
-                                       float* loss, double* lr) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  for (int i = 0; i < 6; ++i) {
-    // sequential semantics returns the clamped parameter; batch semantics the pre-clamp copy (omniloc.py:260,272)
-    if (pose) pose[6 * b + i] = batch ? evalp[6 * b + i] : st[b].param[i];
-    if (param) param[6 * b + i] = st[b].param[i];
-  }
-  if (loss) loss[b] = st[b].last_loss;
-  if (lr) lr[b] = st[b].lr;
-}
-
-extern "C" int pcl_refine_create(int b, double lr, double factor, int patience, int batch_semantics, pcl_refine** out) {
-  if (!out || b <= 0 || b > 65536) { pcl_set_error("bad refine batch %d", b); return PCL_ERR_INVALID; }
-  pcl_refine* r = (pcl_refine*)calloc(1, sizeof(pcl_refine));
-  r->B = b; r->lr0 = lr; r->factor = factor; r->patience = patience; r->batch_semantics = batch_semantics ? 1 : 0;
-  *out = r;                          // device storage is allocated by the first pcl_refine_reset, on its stream
-  return PCL_OK;
-}
-
-extern "C" int pcl_refine_reset(pcl_refine* r, const float* poses_b6_dev, void* stream) {
-  if (!r || !poses_b6_dev) { pcl_set_error("null refine handle or poses"); return PCL_ERR_INVALID; }
-  cudaStream_t st = (cudaStream_t)stream;
-  const size_t b = (size_t)r->B;
-  const size_t o_eval = (sizeof(PclRefineState) * b + 255) & ~(size_t)255;
-  const size_t o_loss = o_eval + ((sizeof(float) * 6 * b + 255) & ~(size_t)255);
-  const size_t o_cnt = o_loss + ((sizeof(float) * b + 255) & ~(size_t)255);
-  if (!r->block) {
-    PCL_CUDA(pcl_pool_alloc((void**)&r->block, o_cnt + sizeof(unsigned int) * b, st));
-    r->owner = st;
-    r->state = (PclRefineState*)r->block;
-    r->evalp = (float*)(r->block + o_eval);
-    r->loss = (float*)(r->block + o_loss);
-    r->counters = (unsigned int*)(r->block + o_cnt);
-  }
-  PCL_CUDA(cudaMemsetAsync(r->counters, 0, sizeof(unsigned int) * b, st));
-  r->steps_done = 0;
-  pcl_refine_reset_kernel<<<(r->B + 127) / 128, 128, 0, st>>>(r->state, r->evalp, poses_b6_dev, r->B, r->lr0);
-  PCL_LAUNCH_CHECK();
-  return PCL_OK;
-}
-
-template <int FMT>
-static cudaError_t pcl_persist_launch_fmt(const PclLaunchPlan& pl, PclCloudView C, PclImage I, int P, PclFinalize fin, PclPersist ps, cudaStream_t st) {
-  int PB = pl.PB;
-  long long n_rows = pl.n_rows;
-  void* args[] = {&C, &I, &P, &PB, &n_rows, &fin, &ps};
-  return cudaLaunchCooperativeKernel((const void*)pcl_refine_persistent_kernel<FMT>, dim3(pl.gx, pl.gy), dim3(PCL_THREADS), args, 0, st);
-}
-
-// returns PCL_OK, an error, or 1 when the cooperative launch is not possible on this device / configuration
-static int pcl_refine_run_persistent(pcl_refine* r, const pcl_cloud* c, const pcl_image* im, const PclLaunchPlan& pl, const PclFinalize& fin,
-                                     int num_iter, cudaStream_t st) {
-  static int coop = -1;
-  if (coop < 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) coop = 0;
-  }
-  if (!coop) return 1;
-  const size_t need = 2 * (size_t)pl.gx * pl.NS * (size_t)r->B;
-  if (need > r->partial_floats) {
-    pcl_pool_free(r->partial, st);
-    r->partial = nullptr; r->partial_floats = 0;
-    PCL_CUDA(pcl_pool_alloc((void**)&r->partial, need * sizeof(double), st));
-    r->partial_floats = need;
-  }
-  if ((size_t)num_iter * 2 > r->bc_cap) {
-    pcl_pool_free(r->bc_dev, st);
-    r->bc_dev = nullptr; r->bc_cap = 0;
-    PCL_CUDA(pcl_pool_alloc((void**)&r->bc_dev, (size_t)num_iter * 2 * sizeof(double), st));
-    r->bc_cap = (size_t)num_iter * 2;
-  }
-  double* bc = (double*)malloc((size_t)num_iter * 2 * sizeof(double));
-  if (!bc) { pcl_set_error("out of host memory"); return PCL_ERR_INVALID; }
-  for (int it = 0; it < num_iter; ++it) {
-    const double step = (double)(r->steps_done + it + 1);
-    bc[2 * it] = 1.0 - pow(0.9, step);
-    bc[2 * it + 1] = sqrt(1.0 - pow(0.999, step));
-  }
-  // pageable source: the call returns once the data is staged, the buffer can be released right away
-  cudaError_t e = cudaMemcpyAsync(r->bc_dev, bc, (size_t)num_iter * 2 * sizeof(double), cudaMemcpyHostToDevice, st);
-  free(bc);
-  PCL_CUDA(e);
-  PCL_CUDA(cudaMemsetAsync(r->counters, 0, sizeof(unsigned int) * (size_t)pl.gy, st));
-  PclPersist ps = {r->partial, r->counters, r->bc_dev, num_iter};
-  PclCloudView C = {c->x, c->y, c->z, c->r, c->g, c->b, (long long)c->n};
-  const PclImage& view = (im->has_small && pcl_env_int("PCL_SMALL_TABLE", 1)) ? im->view_small : im->view;
-  switch (view.fmt) {
-    case PCL_FMT_U8Q: e = pcl_persist_launch_fmt<PCL_FMT_U8Q>(pl, C, view, r->B, fin, ps, st); break;
-    case PCL_FMT_U8P: e = pcl_persist_launch_fmt<PCL_FMT_U8P>(pl, C, view, r->B, fin, ps, st); break;
-    case PCL_FMT_F32: e = pcl_persist_launch_fmt<PCL_FMT_F32>(pl, C, view, r->B, fin, ps, st); break;
-    case PCL_FMT_TEX: e = pcl_persist_launch_fmt<PCL_FMT_TEX>(pl, C, view, r->B, fin, ps, st); break;
-    case PCL_FMT_F16D: e = pcl_persist_launch_fmt<PCL_FMT_F16D>(pl, C, view, r->B, fin, ps, st); break;
-    default: pcl_set_error("unknown image format %d", view.fmt); return PCL_ERR_INVALID;
-  }
-  if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) { (void)cudaGetLastError(); return 1; }
-  g_pcl_launches.fetch_add(1);
-  PCL_CUDA(e);
-  PCL_CUDA(cudaMemsetAsync(r->counters, 0, sizeof(unsigned int) * (size_t)pl.gy, st));     // tickets of the per-iteration path start at zero
-  r->steps_done += num_iter;
-  return PCL_OK;
-}
-
-extern "C" int pcl_refine_run(pcl_refine* r, const pcl_cloud* c, const pcl_image* im, int num_iter, void* stream) {
-  if (!r || !r->block) { pcl_set_error("refine handle is null or was never reset"); return PCL_ERR_INVALID; }
+int pcl_generic_refine_iters(pcl_refine* r, const pcl_cloud* c, const pcl_image* im, int num_iter, cudaStream_t st) {
   int rc = pcl_check_inputs(c, im, r->evalp, r->B);
   if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
   const PclLaunchPlan pl = pcl_plan(c, r->B, true);
   const size_t need = (size_t)pl.gx * pl.NS * (size_t)r->B;
   if (need > r->partial_floats) {
     pcl_pool_free(r->partial, st);
+    r->partial = nullptr; r->partial_floats = 0;
     PCL_CUDA(pcl_pool_alloc((void**)&r->partial, need * sizeof(double), st));
     r->partial_floats = need;
   }
@@ -690,35 +467,13 @@ extern "C" int pcl_refine_run(pcl_refine* r, const pcl_cloud* c, const pcl_image
   fin.loss = r->loss; fin.state = r->state; fin.evalp = r->evalp;
   fin.box = c->lo_hi_dev;
   fin.factor = r->factor; fin.patience = r->patience; fin.batch_semantics = r->batch_semantics;
-  // small batches whose grid is one resident wave: all iterations in one cooperative launch
-  if (num_iter >= 2 && pl.PB <= 16 && (long long)pl.gx * pl.gy <= (long long)pcl_num_sms() * 2 && pcl_env_int("PCL_PERSIST", 1) != 0) {
-    rc = pcl_refine_run_persistent(r, c, im, pl, fin, num_iter, st);
-    if (rc != 1) return rc;              // 1: the device refused the cooperative launch -> per-iteration launches below
-  }
   for (int it = 0; it < num_iter; ++it) {
     r->steps_done += 1;
     fin.bc1 = 1.0 - pow(0.9, (double)r->steps_done);
     fin.bc2_sqrt = sqrt(1.0 - pow(0.999, (double)r->steps_done));
     // iterations after the first opt in to programmatic dependent launch (prologue overlaps the previous tail)
-    rc = pcl_launch<true>(pl, c, im, r->evalp, r->B, r->partial, r->counters, fin, st, it > 0 && pcl_env_int("PCL_PDL", 1) != 0);
+    rc = pcl_launch<true>(pl, c, im, r->evalp, r->B, r->partial, r->counters, fin, st, it > 0 && pcl_opt(PCL_OPT_PDL) != 0);
     if (rc) return rc;
   }
   return PCL_OK;
-}
-
-extern "C" int pcl_refine_read(const pcl_refine* r, float* pose_b6_dev, float* param_b6_dev, float* loss_b_dev,
-                               double* lr_b_dev, void* stream) {
-  if (!r || !r->block) { pcl_set_error("refine handle is null or was never reset"); return PCL_ERR_INVALID; }
-  pcl_refine_read_kernel<<<(r->B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(r->state, r->evalp, r->B, r->batch_semantics,
-                                                                                pose_b6_dev, param_b6_dev, loss_b_dev, lr_b_dev);
-  PCL_LAUNCH_CHECK();
-  return PCL_OK;
-}
-
-extern "C" void pcl_refine_destroy(pcl_refine* r) {
-  if (!r) return;
-  pcl_pool_free(r->block, r->owner);
-  pcl_pool_free(r->partial, r->owner);
-  pcl_pool_free(r->bc_dev, r->owner);
-  free(r);
 }

@@ -23,6 +23,17 @@ def shard_bounds(n: int, rank: int, world_size: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def _all_gather_stack(local: torch.Tensor) -> torch.Tensor:
+    """(…) per rank -> (world, …) on every rank: ONE collective into one preallocated tensor (the list API of
+    dist.all_gather allocates and copies one tensor per rank).  The output is passed in its concatenated form,
+    which both NCCL and gloo accept."""
+    ws = dist.get_world_size()
+    flat = local.contiguous().reshape(-1)
+    out = torch.empty(ws * flat.numel(), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, flat)
+    return out.reshape((ws,) + tuple(local.shape))
+
+
 def _all_gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
     """All-gather variable-length row blocks (contiguous shards) into the full (n_total, ...) tensor."""
     rank, ws = world()
@@ -31,8 +42,7 @@ def _all_gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
     rows = max(shard_bounds(n_total, r, ws)[1] - shard_bounds(n_total, r, ws)[0] for r in range(ws))
     pad = torch.zeros((rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
-    out = [torch.empty_like(pad) for _ in range(ws)]
-    dist.all_gather(out, pad)
+    out = _all_gather_stack(pad)
     parts = []
     for r in range(ws):
         lo, hi = shard_bounds(n_total, r, ws)
@@ -64,14 +74,32 @@ def refine_sharded(refine_fn: Callable[[torch.Tensor], torch.Tensor], starts: to
     rows = (B + ws - 1) // ws
     pad = torch.full((rows, 7), float("nan"), dtype=starts.dtype, device=starts.device)
     pad[: local.shape[0]] = local
-    out = [torch.empty_like(pad) for _ in range(ws)]
-    dist.all_gather(out, pad)
+    out = _all_gather_stack(pad)
     table = torch.empty((B, 7), dtype=starts.dtype, device=starts.device)
     for r in range(ws):
         idx = list(range(r, B, ws))
         if idx:
             table[idx] = out[r][: len(idx)]
     return table
+
+
+_PEER_COMM = None
+
+
+def peer_comm():
+    """The process group's PeerComm (created on first use; the 64-byte IPC handles travel through
+    torch.distributed.all_gather_object, i.e. the host side of NCCL/gloo — set-up only)."""
+    global _PEER_COMM
+    if _PEER_COMM is None:
+        from . import engine
+        rank, ws = world()
+
+        def exchange(mine: bytes):
+            out = [None] * ws
+            dist.all_gather_object(out, mine)
+            return out
+        _PEER_COMM = engine.PeerComm(rank, ws, exchange)
+    return _PEER_COMM
 
 
 def argmin_candidate(table: torch.Tensor):
@@ -86,6 +114,4 @@ def gather_results(row: torch.Tensor) -> torch.Tensor:
     rank, ws = world()
     if ws == 1:
         return row[None]
-    out = [torch.empty_like(row) for _ in range(ws)]
-    dist.all_gather(out, row)
-    return torch.stack(out)
+    return _all_gather_stack(row)

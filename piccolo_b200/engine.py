@@ -205,9 +205,14 @@ class Refiner:
             _lib.check(_lib.load().pcl_refine_reset(self._h, p.data_ptr(), _stream(p.device)))
         return self
 
-    def run(self, cloud: Cloud, image: Image, num_iter: int):
+    def run(self, cloud: Cloud, image: Image, num_iter: int, comm: "PeerComm" = None):
+        """comm: a connected PeerComm -> the POINTS of the cloud are sharded over its ranks (every rank passes the same
+        cloud, image and start poses; the per-CTA partial sums travel as peer stores over NVLink inside the kernel)."""
         with torch.cuda.device(self.device):
-            _lib.check(_lib.load().pcl_refine_run(self._h, cloud._h, image._h, int(num_iter), _stream(self.device)))
+            if comm is not None and comm.size > 1:
+                _lib.check(_lib.load().pcl_refine_run_sharded(self._h, cloud._h, image._h, int(num_iter), comm._h, _stream(self.device)))
+            else:
+                _lib.check(_lib.load().pcl_refine_run(self._h, cloud._h, image._h, int(num_iter), _stream(self.device)))
         return self
 
     def read(self):
@@ -226,6 +231,50 @@ class Refiner:
         if h:
             try:
                 _lib.load().pcl_refine_destroy(h)
+            except Exception:
+                pass
+
+
+class PeerComm:
+    """Peer-memory communicator of the ranks of one box (include/piccolo_b200.h: pcl_comm_*): every rank owns a
+    device window that the others map through CUDA IPC; kernels then exchange data by stores and system-scope
+    atomics over NVLink.  `exchange` is any callable that all-gathers one bytes object per rank in rank order
+    (piccolo_b200.dist.peer_comm() passes torch.distributed.all_gather_object)."""
+
+    def __init__(self, rank: int, size: int, exchange, device=None, window_bytes: int = 0):
+        lib = _lib.load()
+        self.rank, self.size = int(rank), int(size)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.pcl_comm_create(self.rank, self.size, int(window_bytes), ctypes.byref(h)))
+            self._h = h
+            if self.size > 1:
+                mine = ctypes.create_string_buffer(64)
+                _lib.check(lib.pcl_comm_handle(h, mine))
+                handles = exchange(mine.raw)
+                if len(handles) != self.size or any(len(x) != 64 for x in handles):
+                    raise _lib.PiccoloError("peer handle exchange returned a malformed list")
+                _lib.check(lib.pcl_comm_connect(h, ctypes.create_string_buffer(b"".join(handles), 64 * self.size)))
+
+    def barrier(self):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().pcl_comm_barrier(self._h, _stream(self.device)))
+
+    def all_gather(self, local: torch.Tensor) -> torch.Tensor:
+        """(n,) float32 on the device -> (size, n): row k is rank k's vector (n <= 16384, equal on all ranks)."""
+        _require_cuda(local, "local")
+        x = _f32c(local).reshape(-1)
+        out = torch.empty(self.size, x.numel(), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().pcl_comm_allgather_f32(self._h, x.data_ptr(), x.numel(), out.data_ptr(), _stream(x.device)))
+        return out
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().pcl_comm_destroy(h)
             except Exception:
                 pass
 

@@ -3,7 +3,7 @@ yaw-only grid:   python scripts/grid_probe.py"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.getcwd())
-from piccolo_b200 import engine, synth
+from piccolo_b200 import _lib, engine, synth
 from piccolo_b200.utils import generate_rot_points, grid_poses
 from scripts.perf_probe import timeit
 
@@ -23,7 +23,7 @@ for name, rot in cases.items():
     rel = ((a - b).abs() / a.abs()).max().item()
     same = torch.equal(engine.topk(a, 50), engine.topk(b, 50))
     for swap in ("0", "1"):
-        os.environ["PCL_SWAP"] = os.environ["PCL_GRID_SWAP"] = swap
+        _lib.set_option("SWAP", int(swap)); _lib.set_option("GRID_SWAP", int(swap))
         ta = timeit(lambda: engine.score(cloud, image, poses), iters=10)
         tb = timeit(lambda: engine.score_grid(cloud, image, trans, rot), iters=10)
         print(f"[{fmt} swap={swap}] {name}: per-pose {ta:.3f} ms ({len(poses)*1e6/ta/1e6:.1f} G/s)  structured {tb:.3f} ms ({len(poses)*1e6/tb/1e6:.1f} G/s)  "

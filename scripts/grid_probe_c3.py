@@ -3,7 +3,7 @@
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.getcwd())
-from piccolo_b200 import engine, synth
+from piccolo_b200 import _lib, engine, synth
 from piccolo_b200.utils import grid_poses
 from scripts.perf_probe import timeit
 
@@ -21,9 +21,9 @@ for fmt in (sys.argv[1:] or ["tex", "u8p", "u8q", "f16d"]):
     a, _ = engine.score(cloud, image, poses)
     b, _ = engine.score_grid(cloud, image, trans, rot)
     ref = a if ref is None else ref
-    os.environ["PCL_SWAP"] = "1"
+    _lib.set_option("SWAP", 1)
     ts = timeit(lambda: engine.score(cloud, image, poses), iters=2, warm=1, repeats=3)
-    os.environ["PCL_SWAP"] = "0"
+    _lib.set_option("SWAP", 0)
     ta = timeit(lambda: engine.score(cloud, image, poses), iters=2, warm=1, repeats=3)
     tb = timeit(lambda: engine.score_grid(cloud, image, trans, rot), iters=2, warm=1, repeats=3)
     ev = len(poses) * N

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from piccolo_b200 import engine, synth  # noqa: E402
+from piccolo_b200 import _lib, engine, synth  # noqa: E402
 
 
 def timeit(fn, iters=5, warm=2, repeats=5):
@@ -65,7 +65,7 @@ def main():
     print(f"FWDBWD B=64 auto: {ms:.3f} ms {64*N/ms/1e6:.1f} G pp/s")
     ref = engine.Refiner(6, 0.1, 0.8, 5, True).reset(cand)
     for pdl in ("1", "0"):
-        os.environ["PCL_PDL"] = pdl
+        _lib.set_option("PDL", int(pdl))
         ms = timeit(lambda: ref.run(cloud, image, 100), iters=3, warm=1)
         print(f"REFINE 100 iters B=6 pdl={pdl}: {ms:.2f} ms  -> {ms/100*1000:.1f} us/iter, {600*N/ms/1e6:.1f} G pp/s")
 

@@ -2,7 +2,7 @@
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.getcwd())
-from piccolo_b200 import engine, synth
+from piccolo_b200 import _lib, engine, synth
 dev = torch.device("cuda:0")
 sc = synth.make_scene(300_000, 512, 1024, seed=3)
 xyz, rgb, img = [torch.from_numpy(a).to(dev) for a in (sc.xyz, sc.rgb, sc.img)]
@@ -13,7 +13,7 @@ for B in (1, 2, 3, 4, 5, 6, 7, 11, 16):
     for batch in (True, False):
         res = {}
         for persist in ("0", "1"):
-            os.environ["PCL_PERSIST"] = persist
+            _lib.set_option("PERSIST", int(persist))
             out = []
             for iters in (3, 40):
                 ref = engine.Refiner(B, 0.1, 0.8, 5, batch).reset(starts[:B]).run(cloud, image, iters)

@@ -34,6 +34,19 @@ WANT = [
     ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected / issue"),
     ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier / issue"),
     ("smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "stall dispatch / issue"),
+    ("smsp__average_warps_issue_stalled_membar_per_issue_active.ratio", "stall membar / issue"),
+    ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall lg_throttle / issue"),
+    ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall mio_throttle / issue"),
+    ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall branch_resolving / issue"),
+    ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall no_instruction / issue"),
+    ("smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio", "stall imc_miss / issue"),
+    ("smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio", "stall sleeping / issue"),
+    ("smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio", "stall tex_throttle / issue"),
+    ("smsp__average_warps_issue_stalled_drain_per_issue_active.ratio", "stall drain / issue"),
+    ("smsp__average_warps_issue_stalled_selected_per_issue_active.ratio", "selected / issue"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1 data-stage wavefronts %"),
+    ("smsp__inst_executed_op_local_ld.sum", "local loads (spill)"),
+    ("smsp__inst_executed_op_local_st.sum", "local stores (spill)"),
 ]
 print(f"# ncu --set full --clock-control none: `{rep.split('/')[-1]}`\n")
 print("| metric | " + " | ".join(f"launch {i}" for i in range(len(data))) + " |")

@@ -87,7 +87,101 @@ def make_color_small():
     print("color_small: lit fraction", float((img8.reshape(-1, 3).sum(1) > 0).mean()), "match range", float(match_img.min()), float(match_img.max()))
 
 
+def _rows_to_index(rows, table, decimals=5):
+    """index of every row of `rows` in `table` (exact match after rounding)"""
+    key = {tuple(np.round(r, decimals)): i for i, r in enumerate(np.asarray(table, dtype=np.float64))}
+    return np.array([key[tuple(np.round(r, decimals))] for r in np.asarray(rows, dtype=np.float64)], dtype=np.int64)
+
+
+def make_variants(ref_omniloc, ref_utils, with_c1=True):
+    """fixture `variants`: how much the REFERENCE ITSELF varies on the discrete decisions of the path when only the
+    floating-point evaluation order / precision changes (1 vs 8 intra-op threads, fp32 vs fp64).  The GPU tests gate
+    "identical top-K" against this measured set instead of a hand-picked slack (VERDICT r1, weak #1)."""
+    from piccolo_b200 import synth, utils as pu
+    out = {}
+
+    def with_threads(n, fn):
+        old = torch.get_num_threads()
+        torch.set_num_threads(n)
+        try:
+            return fn()
+        finally:
+            torch.set_num_threads(old)
+
+    def with_dtype(dtype, fn):
+        torch.set_default_dtype(dtype)
+        try:
+            return fn()
+        finally:
+            torch.set_default_dtype(torch.float32)
+
+    # ---- (1) trim_input_loss on the 5 x 24 lattice grid of score_lattice ---------------------------------------
+    small = np.load(os.path.join(HERE, "loss_small.npz"))
+    lat = np.load(os.path.join(HERE, "score_lattice.npz"))
+    xyz, rgb, img = small["xyz"], synth.rgb_from_u8(small["rgb8"]), synth.img_from_u8(small["img8"])
+    trans, rot = lat["trans"], lat["rot"]
+    grid = np.concatenate([np.repeat(trans, len(rot), 0), np.tile(rot, (len(trans), 1))], 1)
+
+    def lattice(dtype):
+        x, c, i = [torch.from_numpy(a).to(dtype) for a in (xyz, rgb, img)]
+        tt, rr = ref_utils.trim_input_loss(i, x, c, torch.from_numpy(trans).to(dtype), torch.from_numpy(rot).to(dtype), 10)
+        idx = _rows_to_index(np.concatenate([tt.numpy(), rr.numpy()], 1), grid)
+        table = np.array([ref_loss_grad(ref_omniloc, xyz, rgb, img, g.astype(np.float64 if dtype == torch.float64 else np.float32), dtype)[0] for g in grid])
+        return idx, table
+    for tag, fn in (("t1", lambda: with_threads(1, lambda: lattice(torch.float32))), ("t8", lambda: with_threads(8, lambda: lattice(torch.float32))),
+                    ("f64", lambda: with_dtype(torch.float64, lambda: lattice(torch.float64)))):
+        idx, table = fn()
+        out["lattice_top10_" + tag], out["lattice_table_" + tag] = idx, table
+    print("variants/lattice: top-10", {t: out["lattice_top10_" + t].tolist() for t in ("t1", "t8", "f64")})
+
+    # ---- (2) trim_input_hist_secondary on rerank_small -----------------------------------------------------------
+    rr = np.load(os.path.join(HERE, "rerank_small.npz"))
+    xh, ch, ih, ph = rr["xyz"], synth.rgb_from_u8(rr["rgb8"]), synth.img_from_u8(rr["img8"]), rr["poses"]
+
+    def rerank(dtype):
+        # geometry in `dtype`; colours and panorama stay fp32 (make_pano writes them into an fp32 image, utils.py:186-190)
+        x, c, i = torch.from_numpy(xh).to(dtype), torch.from_numpy(ch), torch.from_numpy(ih)
+        t, r = ref_utils.trim_input_hist_secondary(i, x, c, torch.from_numpy(ph[:, :3].copy()).to(dtype), torch.from_numpy(ph[:, 3:].copy()).to(dtype),
+                                                   len(ph), 4, 4)
+        return _rows_to_index(np.concatenate([t.numpy(), r.numpy()], 1), ph)
+    out["rerank_order_t1"] = with_threads(1, lambda: rerank(torch.float32))
+    out["rerank_order_t8"] = with_threads(8, lambda: rerank(torch.float32))
+    out["rerank_order_f64"] = with_dtype(torch.float64, lambda: rerank(torch.float64))
+    print("variants/rerank: top-6", {t: out["rerank_order_" + t][:6].tolist() for t in ("t1", "t8", "f64")})
+
+    # ---- (3) the complete C1 query: make_input + six omniloc runs -------------------------------------------------
+    if with_c1:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_parse_cfg", os.path.join(REF, "parse_utils.py"))
+        ref_parse = importlib.util.module_from_spec(spec); spec.loader.exec_module(ref_parse)
+        import localize as ref_localize
+        sc1 = synth.make_scene(200000, 512, 1024, seed=3)
+        cfg1 = ref_parse.parse_ini(os.path.join(REF, "configs", "stanford.ini"))
+        init1 = ref_localize.get_init_dict(cfg1)
+
+        def c1(dtype):
+            x1, c1_, i1 = [torch.from_numpy(a).to(dtype) for a in (sc1.xyz, sc1.rgb, sc1.img)]
+            np.random.seed(2); torch.manual_seed(2)
+            in_t, in_r = ref_utils.make_input(i1, x1, c1_, cfg1.num_input, init1, cfg1.criterion, cfg1.num_intermediate)
+            st_t, st_r = in_t.clone(), in_r.clone()
+            res = [ref_omniloc.omniloc(i1, x1, c1_, in_t, in_r, k, cfg1, None) for k in range(cfg1.num_input)]
+            return {"input_trans": st_t.numpy().astype(np.float64), "input_rot": st_r.numpy().astype(np.float64),
+                    "final_t": np.stack([r[0].detach().numpy().reshape(3) for r in res]).astype(np.float64),
+                    "final_R": np.stack([r[1].detach().numpy() for r in res]).astype(np.float64),
+                    "final_loss": np.array([float(r[2]) for r in res]), "best": int(np.argmin([float(r[2]) for r in res]))}
+        for tag, fn in (("t4", lambda: with_threads(4, lambda: c1(torch.float32))), ("f64", lambda: with_dtype(torch.float64, lambda: c1(torch.float64)))):
+            r = fn()
+            for k, v in r.items():
+                out["c1_" + k + "_" + tag] = v
+            print("variants/c1", tag, "best", r["best"], "t", r["final_t"][r["best"]], "losses", np.round(r["final_loss"], 4).tolist(), flush=True)
+    np.savez_compressed(os.path.join(HERE, "variants.npz"), **out)
+
+
 def main():
+    if "variants" in sys.argv[1:]:
+        ref_omniloc, ref_utils = import_reference()
+        make_variants(ref_omniloc, ref_utils, with_c1="noc1" not in sys.argv[1:])
+        return
     if "color" in sys.argv[1:]:
         make_color_small()
         return

@@ -21,7 +21,7 @@ def test_header_symbols_are_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert set(_lib.SIGNATURES) == set(names), set(_lib.SIGNATURES) ^ set(names)
-    assert lib.pcl_abi_version() == 1
+    assert lib.pcl_abi_version() == 2
     assert lib.pcl_launch_count() >= 0
 
 
@@ -50,3 +50,15 @@ def test_no_cpu_fallback_in_python_api():
     for f in os.listdir(pkg):
         if f.endswith(".py"):
             assert "oracle" not in open(os.path.join(pkg, f)).read().replace("# oracle", ""), f
+
+
+def test_options_and_communicator_arguments_are_validated():
+    from piccolo_b200 import _lib
+    lib = _lib.load()
+    assert lib.pcl_set_option(b"PERSIST", 1) == 0 and lib.pcl_set_option(b"persist", -1) == 0
+    assert lib.pcl_set_option(b"NO_SUCH_KNOB", 1) == -1 and b"unknown option" in lib.pcl_last_error()
+    h = ctypes.c_void_p()
+    assert lib.pcl_comm_create(3, 2, 0, ctypes.byref(h)) == -1          # rank outside the communicator
+    assert lib.pcl_comm_create(0, 9, 0, ctypes.byref(h)) == -1          # more ranks than one box has GPUs
+    assert lib.pcl_comm_barrier(None, None) == -1
+    assert lib.pcl_refine_run_sharded(None, None, None, 1, None, None) == -1
