@@ -76,7 +76,8 @@ int64_t pcl_launch_count(void);
  * environment; value < 0 restores the default): PERSIST (1: small refinement batches run all iterations in one
  * cooperative launch), PDL (programmatic dependent launch of per-iteration launches), PB_FWD / PB_BWD (poses per
  * CTA of the generic kernels, 0 = auto), WAVES, SWAP, GRID_SWAP (block order), SMALL_TABLE (compact texel table for
- * small gradient batches), RF_NPB (candidates per pose block of the fused refinement, 0 = auto). */
+ * small gradient batches), RF_NPB (candidates per pose block of the fused refinement, 0 = auto),
+ * RF_DEBUG (1: record per-warp cycle counters, see pcl_refine_debug_stats). */
 int pcl_set_option(const char* name, int value);
 
 /* ---- coloured point cloud ------------------------------------------------------------------ */
@@ -169,6 +170,10 @@ int pcl_refine_run_sharded(pcl_refine* r, const pcl_cloud* c, const pcl_image* i
  * lr_b_dev (nullable, double): current learning rates */
 int pcl_refine_read(const pcl_refine* r, float* pose_b6_dev, float* param_b6_dev, float* loss_b_dev,
                     double* lr_b_dev, void* stream);
+/* Diagnostics (option RF_DEBUG=1 before the run): cycle counters of the last persistent run per compute CTA:
+ * out_host[cta*2 + 0] = cycles inside phases, [cta*2 + 1] = cycles waiting for the next poses.  Returns the number of
+ * compute CTAs recorded (0: nothing recorded) or a negative pcl_status; blocks on `stream`. */
+int pcl_refine_debug_stats(const pcl_refine* r, unsigned long long* out_host, int max_ctas, void* stream);
 void pcl_refine_destroy(pcl_refine* r);
 
 /* ---- peer-memory communicator of the ranks of one box (one process per GPU) ---------------------------------- */

@@ -41,6 +41,7 @@ SIGNATURES = {
     "pcl_refine_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "pcl_refine_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "pcl_refine_run_sharded": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "pcl_refine_debug_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "pcl_refine_destroy": (None, [ctypes.c_void_p]),
     "pcl_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "pcl_comm_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, c_void_pp]),
@@ -72,10 +73,12 @@ def load() -> ctypes.CDLL:
             "(or __graft_entry__.build()). piccolo_b200 has no CPU fallback.")
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if "PCL_LIB" in os.environ and not hasattr(lib, name):
+            continue                     # A/B testing of an older build (scripts/ab_refine.py): newer entry points are absent
         fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.pcl_abi_version() != 2:
+    if lib.pcl_abi_version() != 2 and "PCL_LIB" not in os.environ:
         raise PiccoloError("libpiccolo_b200.so ABI version mismatch")
     _lib = lib
     return lib

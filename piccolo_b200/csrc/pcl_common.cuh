@@ -23,7 +23,7 @@ extern std::atomic<long long> g_pcl_launches;
 int pcl_num_sms();
 // process-global tuning knobs (pcl_set_option / PCL_<NAME> in the environment, read once)
 enum { PCL_OPT_PERSIST = 0, PCL_OPT_PDL, PCL_OPT_PB_FWD, PCL_OPT_PB_BWD, PCL_OPT_WAVES, PCL_OPT_SWAP, PCL_OPT_GRID_SWAP, PCL_OPT_SMALL_TABLE,
-       PCL_OPT_RF_NPB, PCL_OPT_COUNT };
+       PCL_OPT_RF_NPB, PCL_OPT_RF_DEBUG, PCL_OPT_COUNT };
 int pcl_opt(int id);
 
 #define PCL_CUDA(expr)                                                                         \
@@ -100,6 +100,9 @@ struct pcl_refine {
   unsigned int* tickets;        // [PCL_RF_MAXBLK] last-block-done tickets of the per-iteration fallback
   double* bc_dev;               // grow-only: per-iteration Adam bias corrections of a persistent run, [num_iter][2]
   size_t bc_cap;
+  unsigned long long* dbg;      // option RF_DEBUG: per compute CTA cycle counters of the last persistent run
+  size_t dbg_cap;
+  int dbg_ctas;
 };
 
 // Peer-memory window of one rank (pcl_comm.cu): cudaMalloc'ed, IPC-mapped into every other rank of the box.

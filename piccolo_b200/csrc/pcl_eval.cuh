@@ -252,26 +252,51 @@ PCL_HD float pcl_half_hi(uint32_t w) {
 #endif
 }
 
+// Raw footprint data as it comes back from memory: fetching (pcl_fetch_raw) is split from unpacking
+// (pcl_basis_from_raw) so that kernels can issue the loads of several evaluations before using any of them.
+template <int FMT> struct PclRaw { PclTaps t; };                       // U8P, F32, TEX: the four taps, converted
+template <> struct PclRaw<PCL_FMT_U8Q> { pcl_u4 e; };                  // {nw, ne, sw, se} RGBA8
+template <> struct PclRaw<PCL_FMT_F16D> { pcl_u4 lo, hi; };            // 16 halves: the basis itself
+
 template <int FMT>
-PCL_HD void pcl_fetch_basis(const PclImage& I, unsigned int idx, float x0f, float y0f, PclBasis& b) {
-  if (FMT == PCL_FMT_F16D) {
+PCL_HD void pcl_fetch_raw(const PclImage& I, unsigned int idx, float x0f, float y0f, PclRaw<FMT>& r) {
+  if constexpr (FMT == PCL_FMT_F16D) {
     // 32-byte entry per footprint: for each channel the four basis values as fp16 (exact small integers):
     // one 256-bit load (one 32-byte sector), one conversion per value, no differences to form
     const pcl_u4* e = reinterpret_cast<const pcl_u4*>(I.data) + 2 * (size_t)idx;
-    pcl_u4 lo, hi;
 #if defined(__CUDA_ARCH__)
     // sm_100 256-bit load (LDG.E.ENL2.256): the whole 32-byte entry in ONE request per lane
     asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(e));
+        : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w) : "l"(e));
 #else
-    lo = PCL_LDG128(e); hi = PCL_LDG128(e + 1);
+    r.lo = PCL_LDG128(e); r.hi = PCL_LDG128(e + 1);
 #endif
-    b.nw[0] = pcl_half_lo(lo.x); b.dxt[0] = pcl_half_hi(lo.x); b.dy0[0] = pcl_half_lo(lo.y); b.ddx[0] = pcl_half_hi(lo.y);
-    b.nw[1] = pcl_half_lo(lo.z); b.dxt[1] = pcl_half_hi(lo.z); b.dy0[1] = pcl_half_lo(lo.w); b.ddx[1] = pcl_half_hi(lo.w);
-    b.nw[2] = pcl_half_lo(hi.x); b.dxt[2] = pcl_half_hi(hi.x); b.dy0[2] = pcl_half_lo(hi.y); b.ddx[2] = pcl_half_hi(hi.y);
+  } else if constexpr (FMT == PCL_FMT_U8Q) {
+    r.e = PCL_LDG128(reinterpret_cast<const pcl_u4*>(I.data) + idx);   // one 16-byte entry per footprint
+  } else {
+    pcl_fetch<FMT>(I, idx, x0f, y0f, r.t);
+  }
+}
+
+template <int FMT>
+PCL_HD void pcl_basis_from_raw(const PclRaw<FMT>& r, PclBasis& b) {
+  if constexpr (FMT == PCL_FMT_F16D) {
+    b.nw[0] = pcl_half_lo(r.lo.x); b.dxt[0] = pcl_half_hi(r.lo.x); b.dy0[0] = pcl_half_lo(r.lo.y); b.ddx[0] = pcl_half_hi(r.lo.y);
+    b.nw[1] = pcl_half_lo(r.lo.z); b.dxt[1] = pcl_half_hi(r.lo.z); b.dy0[1] = pcl_half_lo(r.lo.w); b.ddx[1] = pcl_half_hi(r.lo.w);
+    b.nw[2] = pcl_half_lo(r.hi.x); b.dxt[2] = pcl_half_hi(r.hi.x); b.dy0[2] = pcl_half_lo(r.hi.y); b.ddx[2] = pcl_half_hi(r.hi.y);
   } else {
     PclTaps t;
-    pcl_fetch<FMT>(I, idx, x0f, y0f, t);
+    if constexpr (FMT == PCL_FMT_U8Q) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        t.nw[c] = pcl_u8_biased(r.e.x, c);
+        t.ne[c] = pcl_u8_biased(r.e.y, c);
+        t.sw[c] = pcl_u8_biased(r.e.z, c);
+        t.se[c] = pcl_u8_biased(r.e.w, c);
+      }
+    } else {
+      t = r.t;
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       b.nw[c] = t.nw[c] - PclTapBias<FMT>::value;          // the only un-biasing
@@ -282,12 +307,28 @@ PCL_HD void pcl_fetch_basis(const PclImage& I, unsigned int idx, float x0f, floa
   }
 }
 
+template <int FMT>
+PCL_HD void pcl_fetch_basis(const PclImage& I, unsigned int idx, float x0f, float y0f, PclBasis& b) {
+  PclRaw<FMT> r;
+  pcl_fetch_raw<FMT>(I, idx, x0f, y0f, r);
+  pcl_basis_from_raw<FMT>(r, b);
+}
+
 // ---------------------------------------------------------------------------------------------
-// one pose·point evaluation
+// one pose·point evaluation, in two halves: A = rigid transform, projection, footprint address;
+// B = blend, mask, residual and (BWD) the camera-frame gradient.  The fetch sits between the two: the fused refinement
+// (pcl_refine.cuh) issues it as an asynchronous copy into shared memory right after A and runs B one pipeline stage
+// later, so the L2 latency of the texel gather never stalls a warp.
 // ---------------------------------------------------------------------------------------------
-template <int FMT, bool BWD>
-PCL_HD void pcl_eval(const PclPose& P, const PclImage& I, float px, float py, float pz,
-                     float cr, float cg, float cb, bool valid, PclAcc& acc) {   // valid: false for padding points
+struct PclMid {
+  float qx, qy, qz, rinv;       // camera-frame point, 1/rho (BWD)
+  float fx, fy;                 // fractional pixel coordinates
+  bool px_pass, py_pass;        // the clip passed the coordinate through (gradient flows)
+};
+struct PclAddr { unsigned int idx; float x0f, y0f; };   // footprint: table entry + integer pixel coordinates
+
+template <bool BWD>
+PCL_HD void pcl_eval_a(const PclPose& P, const PclImage& I, float px, float py, float pz, PclMid& M, PclAddr& A) {
   // q = R (p - t)
   const float dx = px - P.tx, dy = py - P.ty, dz = pz - P.tz;
   const float qx = fmaf(P.r02, dz, fmaf(P.r01, dy, P.r00 * dx));
@@ -306,17 +347,25 @@ PCL_HD void pcl_eval(const PclPose& P, const PclImage& I, float px, float py, fl
   const float ix = fminf(fmaxf(ix_raw, I.ix_lo), I.ix_hi);
   const float iy = fminf(fmaxf(iy_raw, I.iy_lo), I.iy_hi);
   const float tx = pcl_floor_magic(ix), ty = pcl_floor_magic(iy);
-  const float fx = ix - (tx - PCL_MAGIC_F);                               // exact fractional parts
-  const float fy = iy - (ty - PCL_MAGIC_F);
+  M.fx = ix - (tx - PCL_MAGIC_F);                               // exact fractional parts
+  M.fy = iy - (ty - PCL_MAGIC_F);
 #if defined(__CUDA_ARCH__)
   const unsigned int xi = __float_as_uint(tx), yi = __float_as_uint(ty);
 #else
   unsigned int xi, yi; { float a = tx, b = ty; memcpy(&xi, &a, 4); memcpy(&yi, &b, 4); }
 #endif
-  const unsigned int idx = yi * (unsigned int)I.pitch + xi - I.idx_bias;
+  A.idx = yi * (unsigned int)I.pitch + xi - I.idx_bias;
+  A.x0f = tx - PCL_MAGIC_F; A.y0f = ty - PCL_MAGIC_F;
+  M.qx = qx; M.qy = qy; M.qz = qz; M.rinv = rinv;
+  M.px_pass = (ix_raw == ix);                                   // clip passes the gradient inclusively at the bound
+  M.py_pass = (iy_raw == iy);
+}
 
+template <int FMT, bool BWD>
+PCL_HD void pcl_eval_b(const PclImage& I, const PclMid& M, const PclRaw<FMT>& raw, float cr, float cg, float cb, bool valid, PclAcc& acc) {   // valid: false for padding points
+  const float fx = M.fx, fy = M.fy;
   PclBasis b;
-  pcl_fetch_basis<FMT>(I, idx, tx - PCL_MAGIC_F, ty - PCL_MAGIC_F, b);
+  pcl_basis_from_raw<FMT>(raw, b);
 
   float d[3], dsdx[3], dsdy[3], ssum = -0.0f;   // -0.0f + x == x exactly: the first add folds away
   bool all_zero = true;
@@ -344,13 +393,17 @@ PCL_HD void pcl_eval(const PclPose& P, const PclImage& I, float px, float py, fl
   acc.sm += m ? 1.0f : 0.0f;
 
   if (BWD) {
+    const float qx = M.qx, qy = M.qy, qz = M.qz, rinv = M.rinv;
+    const float xp = qx + 1e-6f, zp = qz + 1e-6f;
+    const float rho2 = fmaf(qx, qx, qy * qy);
+    const float rho = rho2 * rinv;
     // g_s = m (s - c)/e ; texel-unit and pixel-unit factors (tex_scale, W/2·(-1/pi), H/2·(2/pi)) are
     // constants of the pose and are applied once to the reduced sums (pcl_finish_gradient).
     const float w = m ? einv : 0.0f;
     float gix = fmaf(d[2], dsdx[2], fmaf(d[1], dsdx[1], d[0] * dsdx[0])) * w;
     float giy = fmaf(d[2], dsdy[2], fmaf(d[1], dsdy[1], d[0] * dsdy[0])) * w;
-    gix = (ix_raw == ix) ? gix : 0.0f;        // clip passes the gradient inclusively at the bound
-    giy = (iy_raw == iy) ? giy : 0.0f;
+    gix = M.px_pass ? gix : 0.0f;
+    giy = M.py_pass ? giy : 0.0f;
     const float dphi = fmaf(xp, xp, qy * qy);
     const float dth = fmaf(zp, zp, rho2);
     // one reciprocal for both denominators.  (dphi or dth == 0 needs qx == -1e-6 exactly; the reference's
@@ -371,6 +424,17 @@ PCL_HD void pcl_eval(const PclPose& P, const PclImage& I, float px, float py, fl
     acc.ty = fmaf(qz, gqx, fmaf(-qx, gqz, acc.ty));
     acc.tz = fmaf(qx, gqy, fmaf(-qy, gqx, acc.tz));
   }
+}
+
+template <int FMT, bool BWD>
+PCL_HD void pcl_eval(const PclPose& P, const PclImage& I, float px, float py, float pz,
+                     float cr, float cg, float cb, bool valid, PclAcc& acc) {
+  PclMid M;
+  PclAddr A;
+  PclRaw<FMT> raw;
+  pcl_eval_a<BWD>(P, I, px, py, pz, M, A);
+  pcl_fetch_raw<FMT>(I, A.idx, A.x0f, A.y0f, raw);
+  pcl_eval_b<FMT, BWD>(I, M, raw, cr, cg, cb, valid, acc);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -136,15 +136,16 @@ static int pcl_refine_run_fused(pcl_refine* r, const pcl_cloud* c, const pcl_ima
   ps.I = view;
   ps.B = r->B;
   pcl_rf_blocks(r->B, &ps.nblk, &ps.npb);
+  ps.rank = rank; ps.nranks = nranks;
+
+  // one resident wave of 2 CTAs per SM = G compute CTAs + the service CTA; small shards get one CTA per 256 points
   ps.p_begin = (long long)c->n * rank / nranks;
   ps.p_end = (long long)c->n * (rank + 1) / nranks;
-  ps.rank = rank; ps.nranks = nranks;
-  // one resident wave of 2 CTAs per SM = G compute CTAs + the service CTA; small shards get one CTA per 256 points
   const long long n_pts = ps.p_end - ps.p_begin;
-  long long G = 2ll * pcl_num_sms() - 1;
-  const long long by_rows = (n_pts + PCL_THREADS - 1) / PCL_THREADS;
+  long long G = (long long)PCL_RF_CTAS_PER_SM * pcl_num_sms() - 1;
+  const long long by_rows = (n_pts + PCL_RF_THREADS - 1) / PCL_RF_THREADS;
   if (G > by_rows) G = by_rows < 1 ? 1 : by_rows;
-  if (comm) G = 2ll * pcl_num_sms() - 1;                   // every rank must use the same G: the record slots are rank*G + cta
+  if (comm) G = (long long)PCL_RF_CTAS_PER_SM * pcl_num_sms() - 1;                   // every rank must use the same G: the record slots are rank*G + cta
   ps.G = (int)G;
   ps.num_iter = num_iter;
   ps.state = r->state; ps.evalp = r->evalp; ps.loss = r->loss;
@@ -188,6 +189,11 @@ static int pcl_refine_run_fused(pcl_refine* r, const pcl_cloud* c, const pcl_ima
       free(bc);
       PCL_CUDA(e);
       ps.bc = r->bc_dev;
+      if (pcl_opt(PCL_OPT_RF_DEBUG)) {
+        rc = pcl_rf_grow((void**)&r->dbg, &r->dbg_cap, (size_t)G * 2, sizeof(unsigned long long), st);
+        if (rc) return rc;
+        ps.dbg = r->dbg; r->dbg_ctas = (int)G;
+      }
       e = pcl_rf_dispatch_persistent(view.fmt, ps, st);
       if (e == cudaSuccess) {
         g_pcl_launches.fetch_add(1);
@@ -255,11 +261,23 @@ extern "C" int pcl_refine_read(const pcl_refine* r, float* pose_b6_dev, float* p
   return PCL_OK;
 }
 
+// Option RF_DEBUG: cycle counters of the last persistent run, out[cta*2 + {0: in phases, 1: waiting for poses}].
+// Returns the number of compute CTAs (0 when nothing was recorded).  Blocks on `stream`.
+extern "C" int pcl_refine_debug_stats(const pcl_refine* r, unsigned long long* out_host, int max_ctas, void* stream) {
+  if (!r || !out_host) { pcl_set_error("null refine handle or output"); return PCL_ERR_INVALID; }
+  if (!r->dbg || r->dbg_ctas <= 0) return 0;
+  const int n = r->dbg_ctas < max_ctas ? r->dbg_ctas : max_ctas;
+  PCL_CUDA(cudaMemcpyAsync(out_host, r->dbg, sizeof(unsigned long long) * 2 * (size_t)n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  PCL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return n;
+}
+
 extern "C" void pcl_refine_destroy(pcl_refine* r) {
   if (!r) return;
   pcl_pool_free(r->block, r->owner);
   pcl_pool_free(r->partial, r->owner);
   pcl_pool_free(r->rec, r->owner);
   pcl_pool_free(r->bc_dev, r->owner);
+  pcl_pool_free(r->dbg, r->owner);
   free(r);
 }

@@ -29,7 +29,12 @@
 #define PCL_RF_MAXNPB 4         // candidates per pose block (their 8 sums live in registers)
 #define PCL_RF_MAXBLK 8
 #define PCL_RF_KK 4             // points per thread per group
-#define PCL_RF_GROUP (PCL_RF_KK * PCL_THREADS)
+#ifndef PCL_RF_THREADS
+#define PCL_RF_THREADS 512      // one CTA of 16 warps per SM (128 registers per thread: the whole register file)
+#endif
+#define PCL_RF_WARPS (PCL_RF_THREADS / 32)
+#define PCL_RF_CTAS_PER_SM (512 / PCL_RF_THREADS)
+#define PCL_RF_GROUP (PCL_RF_KK * PCL_RF_THREADS)
 #define PCL_RF_FLUSH 8          // groups between two flushes of the fp32 register sums into the fp64 shared-memory row
 #define PCL_RF_MAXRANKS 8
 
@@ -40,6 +45,7 @@ struct PclRfParams {
   long long p_begin, p_end;     // this rank's point range
   int G;                        // CTAs per rank
   int rank, nranks;
+  unsigned long long* dbg;      // nullable: per compute CTA {cycles in phases, cycles waiting for poses} (option RF_DEBUG)
   double* rec[PCL_RF_MAXRANKS];           // record buffers of all ranks (rec[rank] is local): [2][nblk][nranks*G][MAXNPB*8]
   unsigned int* arrive[PCL_RF_MAXRANKS];  // arrival counters of all ranks: [nblk], monotonic
   unsigned int arrive_base[PCL_RF_MAXBLK];   // value of block b's counter when this run starts
@@ -57,14 +63,18 @@ struct PclRfParams {
   int patience, batch_semantics;
 };
 
-__device__ __forceinline__ unsigned int pcl_ld_acquire_gpu(const unsigned int* p) {
+// Flag polls are RELAXED loads (served by L2): an acquire load makes the SM invalidate its whole L1 (CCTL.IVALL in the
+// SASS) on every poll, which throws away the texel lines the co-resident compute warps live on.  Everything published
+// behind a flag (records, poses) is read with ld.global.cg, i.e. from L2, after the poll has returned the flag value, and
+// was made visible there by the writer's release before it raised the flag.
+__device__ __forceinline__ unsigned int pcl_ld_poll_gpu(const unsigned int* p) {
   unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ unsigned int pcl_ld_acquire_sys(const unsigned int* p) {
+__device__ __forceinline__ unsigned int pcl_ld_poll_sys(const unsigned int* p) {
   unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -131,7 +141,7 @@ __device__ __forceinline__ void pcl_rf_phase(const PclCloudView& C, const PclIma
     float px[PCL_RF_KK], py[PCL_RF_KK], pz[PCL_RF_KK], cr[PCL_RF_KK], cg[PCL_RF_KK], cb[PCL_RF_KK];
 #pragma unroll
     for (int j = 0; j < PCL_RF_KK; ++j) {
-      const long long i = i0 + (long long)j * PCL_THREADS;
+      const long long i = i0 + (long long)j * PCL_RF_THREADS;
       px[j] = __ldg(C.x + i); py[j] = __ldg(C.y + i); pz[j] = __ldg(C.z + i);
       cr[j] = __ldg(C.r + i); cg[j] = __ldg(C.g + i); cb[j] = __ldg(C.b + i);
     }
@@ -157,7 +167,7 @@ __device__ __forceinline__ void pcl_rf_phase(const PclCloudView& C, const PclIma
   const long long rem0 = c_begin + n_groups * PCL_RF_GROUP;
   const int r = (int)(c_end - rem0);
   if (r > 0) {
-    const int S = PCL_THREADS / np;
+    const int S = PCL_RF_THREADS / np;
     const int p_t = tid % np, slot = tid / np;
     PclAcc ar;
     pcl_rf_zero(ar);
@@ -198,7 +208,7 @@ __device__ __forceinline__ double pcl_rf_cta_sum(double (*s_acc)[NPB][PCL_NSUM],
   const int p = tid >> 3, s = tid & 7;
   double t = 0.0;
 #pragma unroll
-  for (int w = 0; w < PCL_WARPS; ++w) t += s_acc[w][p][s];
+  for (int w = 0; w < PCL_RF_WARPS; ++w) t += s_acc[w][p][s];
   return t;
 }
 
@@ -218,7 +228,7 @@ __device__ __forceinline__ void pcl_rf_finalize(const double* __restrict__ rec, 
                                                 PclRefineState* __restrict__ st, float* __restrict__ evalp, PclPose* __restrict__ pose,
                                                 const PclImage& I, const PclRfConsts& k, const double bc1, const double bc2_sqrt, const int tid) {
   const int nitems = np * (PCL_NSUM / 2);                        // 16-byte pairs of sums
-  const int GG = PCL_THREADS / nitems;
+  const int GG = PCL_RF_THREADS / nitems;
   {
     const int item = tid % nitems, g = tid / nitems;
     double2 t = make_double2(0.0, 0.0);
@@ -294,15 +304,15 @@ __device__ __forceinline__ void pcl_rf_finalize(const double* __restrict__ rec, 
 // persistent kernel: ALL iterations in one cooperative launch; CTA G (the last one) is the service CTA
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pcl_rf_spin(const unsigned int* ctr, const unsigned int target, const bool sys, const unsigned int ns) {
-  if (sys) { while ((int)(pcl_ld_acquire_sys(ctr) - target) < 0) { if (ns) __nanosleep(ns); } }
-  else { while ((int)(pcl_ld_acquire_gpu(ctr) - target) < 0) { if (ns) __nanosleep(ns); } }
+  if (sys) { while ((int)(pcl_ld_poll_sys(ctr) - target) < 0) { if (ns) __nanosleep(ns); } }
+  else { while ((int)(pcl_ld_poll_gpu(ctr) - target) < 0) { if (ns) __nanosleep(ns); } }
 }
 
 template <int FMT, int NPB>
-__global__ void __launch_bounds__(PCL_THREADS, 2) pcl_refine_persistent_kernel(const PclRfParams ps) {
+__global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine_persistent_kernel(const PclRfParams ps) {
   __shared__ __align__(16) PclPose s_pose[2][PCL_RF_MAXB];       // compute: [phase parity][NPB] used; service: [0][B]
-  __shared__ double s_acc[2][PCL_WARPS][NPB][PCL_NSUM];
-  __shared__ double2 s_sum[PCL_THREADS];
+  __shared__ double s_acc[2][PCL_RF_WARPS][NPB][PCL_NSUM];
+  __shared__ double2 s_sum[PCL_RF_THREADS];
   __shared__ PclRefineState s_state[PCL_RF_MAXB];                // service CTA only
   __shared__ float s_evalp[PCL_RF_MAXB][6];
   __shared__ int s_pref[2];                                      // phase whose poses sit in s_pose[parity]
@@ -332,9 +342,8 @@ __global__ void __launch_bounds__(PCL_THREADS, 2) pcl_refine_persistent_kernel(c
                         __ldg(ps.bc + 2 * it), __ldg(ps.bc + 2 * it + 1), tid);
         if (tid < np * 12) ps.posebuf[(size_t)p0 * 12 + tid] = reinterpret_cast<const float*>(&s_pose[0][p0])[tid];
         __syncthreads();
-        if (tid == 0) {
-          __threadfence();
-          const unsigned int v = ps.ready_base[b] + (unsigned int)(it + 1);
+        if (tid == 0) {                                            // release is cumulative over the barrier above; no fence:
+          const unsigned int v = ps.ready_base[b] + (unsigned int)(it + 1);   // a gpu-scope fence would also invalidate this SM's L1
           asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ps.ready + b), "r"(v) : "memory");
         }
       }
@@ -358,10 +367,12 @@ __global__ void __launch_bounds__(PCL_THREADS, 2) pcl_refine_persistent_kernel(c
   __syncthreads();
 
   int ph = 0;
+  long long t_busy = 0, t_wait = 0;
   for (int it = 0; it < ps.num_iter; ++it) {
     for (int b = 0; b < ps.nblk; ++b, ++ph) {
       const int buf = ph & 1;
       const int p0 = b * ps.npb, np = min(ps.npb, ps.B - p0);
+      const long long c0 = ps.dbg ? clock64() : 0;
       if (it == 0) {
         if (tid < np) pcl_pose_from_params(ps.evalp + 6 * (size_t)(p0 + tid), s_pose[buf][tid]);
         __syncthreads();
@@ -374,16 +385,18 @@ __global__ void __launch_bounds__(PCL_THREADS, 2) pcl_refine_persistent_kernel(c
       // the last warp tries to fetch the NEXT phase's poses while the others are still in this phase
       const int nb = (b + 1 == ps.nblk) ? 0 : b + 1, nit = (b + 1 == ps.nblk) ? it + 1 : it;
       auto hook = [&]() {
-        if (warp != PCL_WARPS - 1 || nit == 0 || nit >= ps.num_iter) return;
+        if (warp != PCL_RF_WARPS - 1 || nit == 0 || nit >= ps.num_iter) return;
         unsigned int ok = 0;
-        if (lane == 0) ok = ((int)(pcl_ld_acquire_gpu(ps.ready + nb) - (ps.ready_base[nb] + (unsigned int)nit)) >= 0) ? 1u : 0u;
+        if (lane == 0) ok = ((int)(pcl_ld_poll_gpu(ps.ready + nb) - (ps.ready_base[nb] + (unsigned int)nit)) >= 0) ? 1u : 0u;
         ok = __shfl_sync(0xffffffffu, ok, 0);
         if (!ok) return;
         const int q0 = nb * ps.npb, nq = min(ps.npb, ps.B - q0);
         for (int i = lane; i < nq * 12; i += 32) reinterpret_cast<float*>(&s_pose[buf ^ 1][0])[i] = __ldcg(ps.posebuf + (size_t)q0 * 12 + i);
         if (lane == 0) s_pref[buf ^ 1] = ph + 1;
       };
+      const long long c1 = ps.dbg ? clock64() : 0;
       pcl_rf_phase<FMT, NPB>(ps.C, ps.I, s_pose[buf], np, c_begin, c_end, s_acc[buf], tid, lane, warp, hook);
+      if (ps.dbg) { t_wait += c1 - c0; t_busy += clock64() - c1; }
       if (warp == 0) {
         if (lane < np * PCL_NSUM) {
           const double t = pcl_rf_cta_sum<NPB>(s_acc[buf], lane);
@@ -391,13 +404,17 @@ __global__ void __launch_bounds__(PCL_THREADS, 2) pcl_refine_persistent_kernel(c
           for (int rk = 0; rk < ps.nranks; ++rk) ps.rec[rk][off] = t;
         }
         __syncwarp();
+        // arrive with RELEASE semantics on the reduction itself (cumulative over the __syncwarp above).  A
+        // __threadfence() here would be an acq_rel fence, whose acquire half invalidates the SM's whole L1 — the
+        // texel and point lines the CTA is about to reuse.
         if (lane < ps.nranks) {
-          if (ps.nranks > 1) { __threadfence_system(); atomicAdd_system(ps.arrive[lane] + b, 1u); }
-          else { __threadfence(); atomicAdd(ps.arrive[0] + b, 1u); }
+          if (ps.nranks > 1) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(ps.arrive[lane] + b) : "memory");
+          else asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ps.arrive[0] + b) : "memory");
         }
       }
     }
   }
+  if (ps.dbg && tid == 0) { ps.dbg[2 * (size_t)cta] = (unsigned long long)t_busy; ps.dbg[2 * (size_t)cta + 1] = (unsigned long long)t_wait; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -405,11 +422,11 @@ __global__ void __launch_bounds__(PCL_THREADS, 2) pcl_refine_persistent_kernel(c
 // phase arithmetic, same record order and the same finalize as the persistent kernel: bit-identical trajectories.
 // ------------------------------------------------------------------------------------------------
 template <int FMT, int NPB>
-__global__ void __launch_bounds__(PCL_THREADS, 2) pcl_refine_iter_kernel(const PclRfParams ps, unsigned int* __restrict__ tickets,
+__global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine_iter_kernel(const PclRfParams ps, unsigned int* __restrict__ tickets,
                                                                          const double bc1, const double bc2_sqrt) {
   __shared__ __align__(16) PclPose s_pose[PCL_RF_MAXNPB];
-  __shared__ double s_acc[PCL_WARPS][NPB][PCL_NSUM];
-  __shared__ double2 s_sum[PCL_THREADS];
+  __shared__ double s_acc[PCL_RF_WARPS][NPB][PCL_NSUM];
+  __shared__ double2 s_sum[PCL_RF_THREADS];
   __shared__ int s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -451,14 +468,14 @@ template <int FMT> cudaError_t pcl_rf_launch_iter(const PclRfParams& ps, unsigne
                    : ps.npb == 2 ? (const void*)pcl_refine_persistent_kernel<FMT, 2>                                                \
                    : ps.npb == 3 ? (const void*)pcl_refine_persistent_kernel<FMT, 3>                                                \
                                  : (const void*)pcl_refine_persistent_kernel<FMT, 4>;                                               \
-    return cudaLaunchCooperativeKernel(fn, dim3(ps.G + 1), dim3(PCL_THREADS), args, 0, st);                                             \
+    return cudaLaunchCooperativeKernel(fn, dim3(ps.G + 1), dim3(PCL_RF_THREADS), args, 0, st);                                             \
   }                                                                                                                                 \
   template <> cudaError_t pcl_rf_launch_iter<FMT>(const PclRfParams& ps, unsigned int* tickets, double bc1, double bc2_sqrt, bool pdl, \
                                                   cudaStream_t st) {                                                                \
     cudaLaunchConfig_t cfg;                                                                                                         \
     memset(&cfg, 0, sizeof(cfg));                                                                                                   \
     cfg.gridDim = dim3(ps.G, ps.nblk);                                                                                              \
-    cfg.blockDim = dim3(PCL_THREADS);                                                                                               \
+    cfg.blockDim = dim3(PCL_RF_THREADS);                                                                                               \
     cfg.stream = st;                                                                                                                \
     cudaLaunchAttribute attr[1];                                                                                                    \
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                                \

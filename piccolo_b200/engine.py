@@ -215,6 +215,16 @@ class Refiner:
                 _lib.check(_lib.load().pcl_refine_run(self._h, cloud._h, image._h, int(num_iter), _stream(self.device)))
         return self
 
+    def debug_stats(self):
+        """Option RF_DEBUG: (ctas, 2) uint64 numpy array {cycles in phases, cycles waiting for poses} of the last persistent run."""
+        import numpy as np
+        buf = np.zeros((512, 2), dtype=np.uint64)
+        with torch.cuda.device(self.device):
+            n = _lib.load().pcl_refine_debug_stats(self._h, buf.ctypes.data, 512, _stream(self.device))
+        if n < 0:
+            _lib.check(n)
+        return buf[:n]
+
     def read(self):
         """Returns dict(pose (B,6), param (B,6), loss (B,), lr (B,) float64) on the device."""
         dev = self.device
