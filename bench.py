@@ -150,6 +150,8 @@ def run_reference(args):
     if rank != 0:
         return
     from piccolo_b200 import pipeline, synth
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm would silently run on ONE core.  Use all host cores.
+    torch.set_num_threads(os.cpu_count() or 1)
     cfg = pipeline.STANFORD_PARALLEL
     sc = synth.make_scene(args.n_points, args.height, 2 * args.height, seed=SCENE_SEED)
     grid = stanford_grid(sc, "cpu").poses()
@@ -180,6 +182,75 @@ def workload_config(args, n_grid, cfg):
 
 
 # --------------------------------------------------------------------------------------------------
+def strong_scaling(args, device, rank, ws):
+    """N > 1 only: ONE query of config C3 (Stanford-area-scale synthetic cloud, 10 M points, 2048x4096 panorama, 4096-pose
+    start grid scored -> top-50 -> histogram re-rank -> 6 candidates x 100 iterations) sharded over all ranks, against the
+    same query on rank 0 alone.  Returns the `strong` object of the JSON line (rank 0) or None."""
+    import torch.distributed as dist
+    from piccolo_b200 import engine, pipeline, synth
+    cfg = pipeline.STANFORD_PARALLEL
+    N, H, side, nyaw = args.strong_points, args.strong_height, 16, 16
+    room = (40.0, 30.0, 3.0)
+    sc = synth.make_scene(N, H, 2 * H, room=room, seed=5)
+    grid_np = synth.pose_grid(room, (side, side, 1), nyaw)
+    xyz, rgb, img, g = [torch.from_numpy(np.ascontiguousarray(a)).to(device) for a in (sc.xyz, sc.rgb, sc.img, grid_np)]
+    grid = pipeline.StartGrid(g[::nyaw, :3], g[:nyaw, 3:])
+    cloud, image = engine.Cloud(xyz, rgb, cfg.out_of_room_quantile), engine.Image(img)
+    names = ["t0", "score0", "score1", "rerank1", "refine0", "refine1", "t1"]
+
+    def timed(fn, steps):
+        out = fn(None)                                      # warm-up (also creates the peer-memory communicator)
+        evs = [{n: torch.cuda.Event(enable_timing=True) for n in names} for _ in range(steps)]
+        dist.barrier(); torch.cuda.synchronize()
+        for e in evs:
+            dist.barrier()                                  # every step starts together: a rank cannot run ahead into the next query
+            e["t0"].record()
+            out = fn(e)
+            e["t1"].record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([[e["t0"].elapsed_time(e["t1"]), e["score0"].elapsed_time(e["score1"]), e["score1"].elapsed_time(e["rerank1"]),
+                            e["refine0"].elapsed_time(e["refine1"])] for e in evs], dtype=torch.float64, device=device).mean(0)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)           # max over ranks, per phase
+        return out, [float(v) for v in ms]
+
+    res = {}
+    for mode in ("points", "candidates"):
+        out, ms = timed(lambda ev, m=mode: pipeline.localize_query_sharded(cloud, image, grid, cfg, img=img, refine=m, timers=ev), args.strong_steps)
+        res[mode] = (out, ms)
+    single = None
+    if rank == 0:                                           # the same query on ONE GPU (the other ranks wait at the barrier below)
+        pipeline.localize_query(cloud, image, grid, cfg, img=img)
+        evs = [{n: torch.cuda.Event(enable_timing=True) for n in names} for _ in range(args.strong_steps)]
+        torch.cuda.synchronize()
+        for e in evs:
+            e["t0"].record()
+            single = pipeline.localize_query(cloud, image, grid, cfg, timers=e, img=img)
+            e["t1"].record()
+        torch.cuda.synchronize()
+        ms1 = np.mean([[e["t0"].elapsed_time(e["t1"]), e["score0"].elapsed_time(e["score1"]), e["score1"].elapsed_time(e["rerank1"]),
+                        e["refine0"].elapsed_time(e["refine1"])] for e in evs], axis=0)
+    dist.barrier()
+    if rank != 0:
+        return None
+    evals = pipeline.query_evals(N, len(grid), cfg)
+    phases = lambda m: {"total": m[0], "score": m[1], "topk_hist_rerank": m[2], "refine": m[3]}
+    obj = {"workload": f"C3: ONE query, {N} points, {H}x{2*H} panorama, {len(grid)}-pose start grid ({side}x{side} translations x {nyaw} yaws, "
+                       f"{room[0]:.0f}x{room[1]:.0f}x{room[2]:.0f} m room), top-{cfg.num_intermediate} -> re-rank -> {cfg.num_input} candidates x {cfg.num_iter} iterations",
+           "n_gpus": ws, "steps": args.strong_steps, "timing": "CUDA events per query, max over ranks; ranks barrier before every query",
+           "single_gpu_ms": phases([float(v) for v in ms1]), "evals_per_query": evals}
+    for mode, (out, ms) in res.items():
+        same = bool(torch.equal(torch.sort(single["start_index"]).values, torch.sort(out["start_index"]).values))
+        obj["sharded_" + mode] = {"ms": phases(ms), "speedup": float(ms1[0] / ms[0]), "efficiency": float(ms1[0] / ms[0] / ws),
+                                  "evals_per_s": evals / (ms[0] * 1e-3), "candidate_set_equal": same,
+                                  "best_loss": float(out["loss"]), "single_gpu_best_loss": float(single["loss"])}
+    lim = max(("score", "topk_hist_rerank", "refine"), key=lambda k: obj["sharded_points"]["ms"][k] * ws / max(obj["single_gpu_ms"][k], 1e-9))
+    obj["limiting_phase"] = lim
+    obj["refine_modes"] = {"points": "every rank refines all candidates over 1/N of the points; per-CTA partial sums exchanged by peer stores over NVLink "
+                                     "inside the persistent kernel (pcl_refine_run_sharded), no collective call",
+                           "candidates": "candidates dealt round-robin over the ranks (6 candidates: at most 6 busy GPUs), one NCCL all-gather of (loss, pose)"}
+    return obj
+
+
 def run_ours(args):
     import torch.distributed as dist
     from piccolo_b200 import _lib, dist as pdist, engine, pipeline, synth
@@ -275,6 +346,12 @@ def run_ours(args):
     e2e_value = ws * q_evals * e2e_steps / (e2e_ms * 1e-3)
     h2d = int(xyz_h.numel() * 4 + rgb_h.numel() * 4 + img_h.numel() * 4 + grid_h.trans.numel() * 4 + grid_h.rot.numel() * 4)
 
+    strong = None
+    if ws > 1 and not args.no_strong:
+        del cloud, image, flush
+        torch.cuda.empty_cache()
+        strong = strong_scaling(args, device, rank, ws)
+
     if rank == 0:
         peak, peak_kind = measured_hbm_peak()
         bwd_launch_s = (sum(refine_ms) / len(refine_ms)) * 1e-3 / cfg.num_iter
@@ -324,6 +401,8 @@ def run_ours(args):
         # `roofline` = the kernel with the larger share of the step (ncu launch list: profiles/r1_launch_list_bench_C2.md); the two
         # phases are within a few per cent of each other at C2, so a near-tie goes to the refinement kernel (the lower fraction)
         line["roofline"] = dict(line["roofline_score"] if sum(score_ms) > 1.1 * sum(refine_ms) else line["roofline_refine"])
+        if strong is not None:
+            line["strong"] = strong
         print(json.dumps(line))
     if ws > 1:
         dist.destroy_process_group()
@@ -338,6 +417,10 @@ def main():
     ap.add_argument("--n-points", type=int, default=1_000_000)
     ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling measurement of one sharded C3 query")
+    ap.add_argument("--strong-points", type=int, default=10_000_000)
+    ap.add_argument("--strong-height", type=int, default=2048)
+    ap.add_argument("--strong-steps", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -119,6 +119,15 @@ int pcl_topk(const float* loss_p_dev, int64_t p, int k, int64_t* idx_k_dev, void
  * panorama.  hist_intersect_k_dev[k] = the reference's `hist_intersect` (larger is better). */
 int pcl_hist_rerank(const pcl_cloud* c, const float* img_hw3_dev, int h, int w, const float* poses_k6_dev, int k,
                     int num_split_h, int num_split_w, float* hist_intersect_k_dev, void* stream);
+/* The same in two stages, for sharding the K candidates over ranks.  Stage 1 is independent per candidate:
+ * rows_k_dev[k][2*nblk] (nblk = (num_split_h-2)*num_split_w; per compared block the histogram intersection, then the
+ * number of lit rendered pixels) and ngt_dev[nblk] (lit query pixels per block, identical on every rank).  Stage 2 replays
+ * the reference's loop over ALL candidates in order (its table persists from one candidate to the next, utils.py:547-579),
+ * so it runs on the rows gathered from all ranks.  num_split_h < 3 leaves no compared block: every score is 0 (reference). */
+int pcl_hist_rerank_blocks(const pcl_cloud* c, const float* img_hw3_dev, int h, int w, const float* poses_k6_dev, int k,
+                           int num_split_h, int num_split_w, float* rows_k_dev, float* ngt_dev, void* stream);
+int pcl_hist_rerank_finish(const float* rows_k_dev, const float* ngt_dev, int k, int num_split_h, int num_split_w,
+                           float* hist_intersect_k_dev, void* stream);
 
 /* ---- colour matching of the panorama to the cloud (color_match, color_utils.py:146-234; localize.py:402-404) ------ */
 /* Both inputs must be uint8/255 data.  pcl_color_stats fills stats_dev (PCL_COLOR_STATS_BYTES, caller-allocated device

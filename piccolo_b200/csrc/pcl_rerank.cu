@@ -2,26 +2,40 @@
 // Replaces trim_input_hist_secondary (utils.py:510-588) = K x { make_pano (utils.py:134-205: sort by distance,
 // nine index_put_ calls), 8 block histograms (color_utils.py:68-119), histogram intersection (:122-144) }.
 //
-// One depth-tested splat for ALL candidates at once: every (candidate, point) issues up to nine 64-bit
-// atomicMax of  key = [write rank:4 | ~distance bits:32 | point index:28]  into a per-candidate key image, which
-// realises the painter's order the reference intends (centre write beats the eight neighbour writes in call
-// order, nearest point wins inside a call) without sorting the cloud per candidate.  A second kernel builds the
-// 8x8x8 colour histogram of every (candidate, block) in shared memory and intersects it with the query's.
+// make_pano paints every point nine times — its centre pixel and the eight neighbours, one index_put_ call per offset,
+// far points first — so the colour of a pixel is decided by (call order, then distance): the LAST call that reaches
+// the pixel wins, and inside a call the nearest point.  All points that reach pixel P in call r have their centre in
+// the same source pixel P - offset_r (plus the clamped copies on the first/last column), hence:
+//   1. splat: ONE 64-bit atomicMax per (candidate, point) of key = [present | ~distance bits:32 | lit:1 | colour bin:9]
+//      into the centre pixel of a per-candidate key image -> the nearest point of every source pixel, carrying the only
+//      two things the histogram needs from it;
+//   2. gather: per output pixel read the 3x3 neighbourhood of keys (nine independent loads) and take the key of the
+//      last call that reached the pixel — no atomics, no second gather of colours — then count its bin in shared memory.
+// (Round 1 issued the nine read+atomicMax per point: 450 M cell visits for 50 candidates x 1 M points, latency-bound.)
 #include "pcl_common.cuh"
 
 #include <string.h>
 
-#define PCL_IDX_BITS 28
-#define PCL_IDX_MASK ((1ull << PCL_IDX_BITS) - 1ull)
+// key of a splatted point: [present:1 | ~distance bits:32 | colour is lit:1 | 8x8x8 colour bin:9].  The nearest point of a
+// pixel has the largest key; what the histogram needs from the winner — its bin and whether it is lit — rides in the low bits,
+// so the gather never has to fetch the point's colour again.
+#define PCL_RR_LOW_BITS 10
+#define PCL_RR_PRESENT (1ull << (32 + PCL_RR_LOW_BITS))
 
 __global__ void pcl_rr_pose_kernel(const float* __restrict__ poses6, int K, PclPose* out) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < K) pcl_pose_from_params(poses6 + 6 * k, out[k]);
 }
 
-// rows [y_lo, y_hi) of the key image are kept (the middle row blocks, the only ones that are compared)
+__device__ __forceinline__ int pcl_rr_bin(float r, float g, float b) {
+  // histogram(): value.long() // ceil(255/8)  with value = colour*255 in fp32 (color_utils.py:84-97)
+  const int br = (int)(long long)(r * 255.0f) / 32, bg = (int)(long long)(g * 255.0f) / 32, bb = (int)(long long)(b * 255.0f) / 32;
+  return br + 8 * bg + 64 * bb;
+}
+
+// rows [ky_lo, ky_hi) of the key image are kept: the compared row blocks plus one source row above and below
 __global__ void pcl_rr_splat_kernel(const PclCloudView C, const PclPose* __restrict__ poses, const int H, const int W,
-                                    const int y_lo, const int y_hi, unsigned long long* __restrict__ keys) {
+                                    const int ky_lo, const int ky_hi, unsigned long long* __restrict__ keys) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= C.n) return;
   const PclPose P = poses[blockIdx.y];
@@ -31,36 +45,69 @@ __global__ void pcl_rr_splat_kernel(const PclCloudView C, const PclPose* __restr
   const float qz = P.r20 * dx + P.r21 * dy + P.r22 * dz;
   // cloud2idx, fp32 op for op (utils.py:44-59) with the kernels' minimax atan2 (1e-7 rad: moves a point across a
   // pixel-truncation boundary with probability ~1e-5), then make_pano's pixel truncation (utils.py:159-165).
-  // Rows first: only the middle row blocks are ever compared, points landing elsewhere stop here.
+  // Rows first: points whose centre row is outside the kept band stop here.
   const float theta = pcl_atan2_pos(sqrtf(qx * qx + qy * qy), qz + 1e-6f);
   const float v = 2.0f * (theta / 3.14159265358979323846f) - 1.0f;
   const int y = (int)(((v + 1.0f) / 2.0f) * (float)(H - 1));
-  if (y + 1 < y_lo || y - 1 >= y_hi) return;
+  if (y < ky_lo || y >= ky_hi) return;
   const float phi = pcl_atan2(qy, qx + 1e-6f) + 3.14159265358979323846f;
   const float u = 2.0f * (1.0f - phi / 6.28318530717958647692f) - 1.0f;
   const int x = (int)(((u + 1.0f) / 2.0f) * (float)(W - 1));
   const float dist = sqrtf(qx * qx + qy * qy + qz * qz);
-  const unsigned long long base = ((unsigned long long)(~__float_as_uint(dist)) << PCL_IDX_BITS) | ((unsigned long long)i & PCL_IDX_MASK);
-  unsigned long long* img = keys + (size_t)blockIdx.y * (size_t)(y_hi - y_lo) * (size_t)W;
-  const int yp = min(y + 1, H - 1), ym = max(y - 1, 0), xp = min(x + 1, W - 1), xm = max(x - 1, 0);
-  // write ranks = call order of utils.py:190-198 (later call overwrites earlier): idx8,7,6,5,4,3,2,1, centre
-  const int ys[9] = {y, y, ym, ym, ym, yp, yp, yp, y};
-  const int xs[9] = {xm, xp, xm, x, xp, xm, x, xp, x};
-#pragma unroll
-  for (int r = 8; r >= 0; --r) {              // centre first: it wins most pixels, later (weaker) keys are filtered by the read
-    if (ys[r] >= y_lo && ys[r] < y_hi) {
-      unsigned long long* cell = img + (size_t)(ys[r] - y_lo) * (size_t)W + (size_t)xs[r];
-      const unsigned long long key = ((unsigned long long)(r + 1) << 60) | base;
-      if (__ldcg(cell) < key) atomicMax(cell, key);      // a stale read only costs a redundant atomic, never a wrong result
-    }
-  }
+  const float r = C.r[i], g = C.g[i], b = C.b[i];
+  const unsigned int lit = !(r * 255.0f == 0.0f && g * 255.0f == 0.0f && b * 255.0f == 0.0f);       // proj_mask (utils.py:554)
+  const unsigned long long key = PCL_RR_PRESENT | ((unsigned long long)(~__float_as_uint(dist)) << PCL_RR_LOW_BITS) |
+                                 (unsigned long long)((lit << 9) | (unsigned int)pcl_rr_bin(r, g, b));
+  unsigned long long* cell = keys + ((size_t)blockIdx.y * (size_t)(ky_hi - ky_lo) + (size_t)(y - ky_lo)) * (size_t)W + (size_t)x;
+  if (__ldcg(cell) < key) atomicMax(cell, key);      // a stale read only costs a redundant atomic, never a wrong result
 }
 
-__device__ __forceinline__ int pcl_rr_bin(float r, float g, float b) {
-  // histogram(): value.long() // ceil(255/8)  with value = colour*255 in fp32 (color_utils.py:84-97)
-  const int br = (int)(long long)(r * 255.0f) / 32, bg = (int)(long long)(g * 255.0f) / 32, bb = (int)(long long)(b * 255.0f) / 32;
-  return br + 8 * bg + 64 * bb;
+// The point make_pano leaves in pixel (y, x): offsets in REVERSE call order (utils.py:190-198: idx8, 7, ..., 1, centre;
+// the last call wins), the first source pixel that holds a key decides.  Source of call (dy, dx) for pixel (y, x) is
+// (y - dy, x - dx); on the first / last column (row) the clamped writes of the pixel itself land there too.
+__device__ __forceinline__ unsigned long long pcl_rr_winner(const unsigned long long* __restrict__ kimg, const int H, const int W,
+                                                            const int ky_lo, const int y, const int x) {
+  // (dy, dx) of the calls, last call first: centre, idx1 (+1,+1), idx2 (+1,0), idx3 (+1,-1), idx4 (-1,+1), idx5 (-1,0),
+  // idx6 (-1,-1), idx7 (0,+1), idx8 (0,-1)
+  const int dys[9] = {0, 1, 1, 1, -1, -1, -1, 0, 0};
+  const int dxs[9] = {0, 1, 0, -1, 1, 0, -1, 1, -1};
+  if (y > 0 && y < H - 1 && x > 0 && x < W - 1) {
+    // interior pixel: exactly one source per call.  All nine loads are issued before the first is examined (neighbouring
+    // pixels share them through L1): nine independent requests instead of a chain of up to nine dependent ones.
+    unsigned long long k[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) k[r] = kimg[(size_t)(y - dys[r] - ky_lo) * W + (x - dxs[r])];
+    unsigned long long best = 0ull;
+#pragma unroll
+    for (int r = 8; r >= 0; --r) best = k[r] ? k[r] : best;      // the earliest r (= the last call) that holds a key wins
+    return best;
+  }
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    const int dy = dys[r], dx = dxs[r];
+    unsigned long long best = 0ull;
+    // candidate source rows / columns: the regular one, and the pixel's own when the write was clamped onto it
+    const int sy0 = y - dy, sx0 = x - dx;
+    const bool y_reg = sy0 >= 0 && sy0 < H, x_reg = sx0 >= 0 && sx0 < W;
+    const bool y_clamp = (dy == 1 && y == H - 1) || (dy == -1 && y == 0);
+    const bool x_clamp = (dx == 1 && x == W - 1) || (dx == -1 && x == 0);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      if (a == 0 ? !y_reg : !y_clamp) continue;
+      const int sy = a == 0 ? sy0 : y;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        if (b == 0 ? !x_reg : !x_clamp) continue;
+        const int sx = b == 0 ? sx0 : x;
+        const unsigned long long k = kimg[(size_t)(sy - ky_lo) * W + sx];
+        best = k > best ? k : best;
+      }
+    }
+    if (best) return best;
+  }
+  return 0ull;
 }
+
 
 // query side, once per image: raw 512-bin histogram counts per compared block (blockIdx.y slices the rows)
 __global__ void pcl_rr_img_hist_kernel(const float* __restrict__ img, const int H, const int W, const int nsh, const int nsw,
@@ -85,31 +132,35 @@ __global__ void pcl_rr_img_hist_kernel(const float* __restrict__ img, const int 
 
 // candidate side: one CTA per (block, candidate)
 __global__ void pcl_rr_cand_hist_kernel(const PclCloudView C, const float* __restrict__ img, const unsigned long long* __restrict__ keys,
-                                        const int H, const int W, const int nsh, const int nsw, const int y_lo, const int y_hi,
+                                        const int H, const int W, const int nsh, const int nsw, const int ky_lo, const int ky_hi,
                                         const unsigned int* __restrict__ img_hist, const unsigned int* __restrict__ n_gt,
-                                        float* __restrict__ inter /*[K][nblk]*/, int* __restrict__ n_tgt) {
+                                        float* __restrict__ rows /*[K][2*nblk]: intersection per block, then lit-pixel count per block*/) {
   __shared__ unsigned int hist[512];
-  __shared__ unsigned int total;
+  __shared__ unsigned int s_total[32];
   __shared__ float red[32];
   const int blk = blockIdx.x, cand = blockIdx.y, nblk = gridDim.x, bh = H / nsh, bw = W / nsw;
   const int h = 1 + blk / nsw, w = blk % nsw;
   for (int i = threadIdx.x; i < 512; i += blockDim.x) hist[i] = 0;
-  if (threadIdx.x == 0) total = 0;
   __syncthreads();
-  const unsigned long long* kimg = keys + (size_t)cand * (size_t)(y_hi - y_lo) * (size_t)W;
+  const unsigned long long* kimg = keys + (size_t)cand * (size_t)(ky_hi - ky_lo) * (size_t)W;
+#pragma unroll 2
   for (int p = threadIdx.x; p < bh * bw; p += blockDim.x) {
     const int y = h * bh + p / bw, x = w * bw + p % bw;
-    const unsigned long long key = kimg[(size_t)(y - y_lo) * W + x];
-    if (key == 0ull) continue;
     const float* px = img + ((size_t)y * W + x) * 3;
-    if (px[0] * 255.0f == 0.0f && px[1] * 255.0f == 0.0f && px[2] * 255.0f == 0.0f) continue;     // img_mask
-    const long long i = (long long)(key & PCL_IDX_MASK);
-    const float r = C.r[i], g = C.g[i], b = C.b[i];
-    if (r * 255.0f == 0.0f && g * 255.0f == 0.0f && b * 255.0f == 0.0f) continue;                  // proj_mask
-    atomicAdd(&hist[pcl_rr_bin(r, g, b)], 1u);
-    atomicAdd(&total, 1u);
+    const float i0 = px[0], i1 = px[1], i2 = px[2];            // independent of the keys: in flight together with them
+    const unsigned long long key = pcl_rr_winner(kimg, H, W, ky_lo, y, x);
+    const bool img_lit = !(i0 * 255.0f == 0.0f && i1 * 255.0f == 0.0f && i2 * 255.0f == 0.0f);       // img_mask
+    if (key != 0ull && img_lit && ((key >> 9) & 1ull)) atomicAdd(&hist[(unsigned int)key & 511u], 1u);
   }
   __syncthreads();
+  // number of lit rendered pixels of the block = sum of the histogram
+  unsigned int cnt = 0;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) cnt += hist[i];
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) s_total[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  unsigned int total = 0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) total += s_total[i];
   float s = 0.0f;
   const float tot = (float)total, gtot = (float)n_gt[blk];      // hist / hist.sum() on both sides (color_utils.py:103)
   for (int i = threadIdx.x; i < 512; i += blockDim.x) s += fminf((float)img_hist[blk * 512 + i] / gtot, (float)hist[i] / tot);
@@ -119,8 +170,8 @@ __global__ void pcl_rr_cand_hist_kernel(const PclCloudView C, const float* __res
   if (threadIdx.x == 0) {
     float t = 0.0f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-    inter[cand * nblk + blk] = t;
-    n_tgt[cand * nblk + blk] = (int)total;
+    rows[(size_t)cand * 2 * nblk + blk] = t;
+    rows[(size_t)cand * 2 * nblk + nblk + blk] = (float)total;       // exact: a block has < 2^24 pixels
   }
 }
 
@@ -128,7 +179,7 @@ __global__ void pcl_rr_cand_hist_kernel(const PclCloudView C, const float* __res
 // block writes 0 and BREAKS the inner (column) loop (cells to its right keep the previous candidate's value),
 // NaN -> 0, mean over ALL nsh*nsw cells.  One thread per table cell walks the candidates in order; the per-
 // candidate sum over cells is a block reduction.  Launch with 64 threads.
-__global__ void pcl_rr_final_kernel(const float* __restrict__ inter, const int* __restrict__ n_tgt, const unsigned int* __restrict__ n_gt,
+__global__ void pcl_rr_final_kernel(const float* __restrict__ rows, const float* __restrict__ n_gt,
                                     const int K, const int nsh, const int nsw, float* __restrict__ out) {
   __shared__ float red[2];
   const int cell = threadIdx.x, ncell = nsh * nsw, nblk = (nsh - 2) * nsw;
@@ -137,13 +188,14 @@ __global__ void pcl_rr_final_kernel(const float* __restrict__ inter, const int* 
   float cur = 0.0f;
   for (int c = 0; c < K; ++c) {
     if (compared) {
+      const float* row = rows + (size_t)c * 2 * nblk;
       // first empty column of this row for this candidate (the `break`)
       int first_empty = nsw;
       for (int ww = 0; ww <= w; ++ww) {
         const int blk = (h - 1) * nsw + ww;
-        if (n_tgt[c * nblk + blk] == 0 || n_gt[blk] == 0u) { first_empty = ww; break; }
+        if (row[nblk + blk] == 0.0f || n_gt[blk] == 0.0f) { first_empty = ww; break; }
       }
-      if (w < first_empty) cur = inter[c * nblk + (h - 1) * nsw + w];
+      if (w < first_empty) cur = row[(h - 1) * nsw + w];
       else if (w == first_empty) cur = 0.0f;
       if (isnan(cur)) cur = 0.0f;
     }
@@ -156,42 +208,87 @@ __global__ void pcl_rr_final_kernel(const float* __restrict__ inter, const int* 
   }
 }
 
-extern "C" int pcl_hist_rerank(const pcl_cloud* c, const float* img_hw3_dev, int h, int w, const float* poses_k6_dev, int k,
-                               int num_split_h, int num_split_w, float* hist_intersect_k_dev, void* stream) {
-  if (!c || !img_hw3_dev || !poses_k6_dev || !hist_intersect_k_dev || k <= 0 || h < 4 || w < 4) { pcl_set_error("bad re-rank arguments"); return PCL_ERR_INVALID; }
-  if (num_split_h < 3 || num_split_w < 1 || num_split_h * num_split_w > 64) { pcl_set_error("num_split_h must be >= 3 and num_split_h*num_split_w <= 64"); return PCL_ERR_INVALID; }
-  if (c->n > (long long)PCL_IDX_MASK) { pcl_set_error("re-rank supports up to 2^28 points"); return PCL_ERR_INVALID; }
+__global__ void pcl_rr_ngt_kernel(const unsigned int* __restrict__ n_gt, int nblk, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nblk) out[i] = (float)n_gt[i];
+}
+
+static int pcl_rr_check_split(int h, int w, int nsh, int nsw) {
+  if (h < 4 || w < 4 || nsh < 1 || nsw < 1 || nsh * nsw > 64 || h / nsh < 1 || w / nsw < 1) {
+    pcl_set_error("bad re-rank geometry: %d x %d panorama, %d x %d blocks (at most 64 blocks)", h, w, nsh, nsw);
+    return PCL_ERR_INVALID;
+  }
+  return PCL_OK;
+}
+
+// Stage 1, independent per candidate (shards over ranks): rows_k_dev[k][2*nblk] = per compared block the histogram
+// intersection, then the number of lit rendered pixels; ngt_dev[nblk] = lit pixels of the query per block.
+extern "C" int pcl_hist_rerank_blocks(const pcl_cloud* c, const float* img_hw3_dev, int h, int w, const float* poses_k6_dev, int k,
+                                      int num_split_h, int num_split_w, float* rows_k_dev, float* ngt_dev, void* stream) {
+  if (!c || !img_hw3_dev || !poses_k6_dev || !rows_k_dev || !ngt_dev || k <= 0) { pcl_set_error("bad re-rank arguments"); return PCL_ERR_INVALID; }
+  int rc = pcl_rr_check_split(h, w, num_split_h, num_split_w);
+  if (rc) return rc;
+  if (num_split_h < 3) return PCL_OK;                     // no compared row blocks (utils.py:548: range(1, nsh-1) is empty): nothing to compute
   cudaStream_t st = (cudaStream_t)stream;
   const int bh = h / num_split_h, nblk = (num_split_h - 2) * num_split_w;
   const int y_lo = bh, y_hi = (num_split_h - 1) * bh;
-  const size_t key_bytes = (size_t)k * (size_t)(y_hi - y_lo) * (size_t)w * sizeof(unsigned long long);
+  const int ky_lo = y_lo - 1, ky_hi = y_hi + 1 < h ? y_hi + 1 : h;       // one source row above and below the compared band
+  const size_t key_bytes = (size_t)k * (size_t)(ky_hi - ky_lo) * (size_t)w * sizeof(unsigned long long);
   const size_t off_pose = (key_bytes + 255) & ~(size_t)255;
   const size_t off_ih = off_pose + (((size_t)k * sizeof(PclPose) + 255) & ~(size_t)255);
   const size_t off_ngt = off_ih + (size_t)nblk * 512 * sizeof(unsigned int);
-  const size_t off_inter = off_ngt + (((size_t)nblk * sizeof(int) + 255) & ~(size_t)255);
-  const size_t off_ntgt = off_inter + (((size_t)k * nblk * sizeof(float) + 255) & ~(size_t)255);
-  const size_t total = off_ntgt + (size_t)k * nblk * sizeof(int);
+  const size_t total = off_ngt + (((size_t)nblk * sizeof(int) + 255) & ~(size_t)255);
   char* buf;
   PCL_CUDA(pcl_pool_alloc((void**)&buf, total, st));
-  PCL_CUDA(cudaMemsetAsync(buf, 0, key_bytes, st));
-  PCL_CUDA(cudaMemsetAsync(buf + off_ih, 0, off_inter - off_ih, st));
+  cudaError_t e = cudaMemsetAsync(buf, 0, key_bytes, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(buf + off_ih, 0, total - off_ih, st);
+  if (e != cudaSuccess) { pcl_pool_free(buf, st); pcl_set_error("re-rank scratch clear failed: %s", cudaGetErrorString(e)); return PCL_ERR_CUDA; }
   unsigned long long* keys = (unsigned long long*)buf;
   PclPose* poses = (PclPose*)(buf + off_pose);
   unsigned int* img_hist = (unsigned int*)(buf + off_ih);
   unsigned int* n_gt = (unsigned int*)(buf + off_ngt);
-  float* inter = (float*)(buf + off_inter);
-  int* n_tgt = (int*)(buf + off_ntgt);
   PclCloudView C = {c->x, c->y, c->z, c->r, c->g, c->b, (long long)c->n};
   pcl_rr_pose_kernel<<<(k + 63) / 64, 64, 0, st>>>(poses_k6_dev, k, poses);
-  PCL_LAUNCH_CHECK();
-  pcl_rr_splat_kernel<<<dim3((unsigned int)((c->n + 255) / 256), k), 256, 0, st>>>(C, poses, h, w, y_lo, y_hi, keys);
-  PCL_LAUNCH_CHECK();
+  pcl_rr_splat_kernel<<<dim3((unsigned int)((c->n + 255) / 256), k), 256, 0, st>>>(C, poses, h, w, ky_lo, ky_hi, keys);
   pcl_rr_img_hist_kernel<<<dim3(nblk, 32), 256, 0, st>>>(img_hw3_dev, h, w, num_split_h, num_split_w, img_hist, n_gt);
-  PCL_LAUNCH_CHECK();
-  pcl_rr_cand_hist_kernel<<<dim3(nblk, k), 512, 0, st>>>(C, img_hw3_dev, keys, h, w, num_split_h, num_split_w, y_lo, y_hi, img_hist, n_gt, inter, n_tgt);
-  PCL_LAUNCH_CHECK();
-  pcl_rr_final_kernel<<<1, 64, 0, st>>>(inter, n_tgt, n_gt, k, num_split_h, num_split_w, hist_intersect_k_dev);
-  PCL_LAUNCH_CHECK();
+  pcl_rr_cand_hist_kernel<<<dim3(nblk, k), 512, 0, st>>>(C, img_hw3_dev, keys, h, w, num_split_h, num_split_w, ky_lo, ky_hi, img_hist, n_gt, rows_k_dev);
+  pcl_rr_ngt_kernel<<<1, 64, 0, st>>>(n_gt, nblk, ngt_dev);
+  g_pcl_launches.fetch_add(5);
+  e = cudaGetLastError();
   pcl_pool_free(buf, st);
+  if (e != cudaSuccess) { pcl_set_error("re-rank launch failed: %s", cudaGetErrorString(e)); return PCL_ERR_CUDA; }
   return PCL_OK;
+}
+
+// Stage 2, over ALL K candidates in their original order (the reference's table persists from one candidate to the next).
+extern "C" int pcl_hist_rerank_finish(const float* rows_k_dev, const float* ngt_dev, int k, int num_split_h, int num_split_w,
+                                      float* hist_intersect_k_dev, void* stream) {
+  if (!rows_k_dev || !ngt_dev || !hist_intersect_k_dev || k <= 0 || num_split_h < 1 || num_split_w < 1 || num_split_h * num_split_w > 64) {
+    pcl_set_error("bad re-rank arguments");
+    return PCL_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (num_split_h < 3) {                                  // reference: every hist_intersect stays 0
+    PCL_CUDA(cudaMemsetAsync(hist_intersect_k_dev, 0, sizeof(float) * (size_t)k, st));
+    return PCL_OK;
+  }
+  pcl_rr_final_kernel<<<1, 64, 0, st>>>(rows_k_dev, ngt_dev, k, num_split_h, num_split_w, hist_intersect_k_dev);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
+
+extern "C" int pcl_hist_rerank(const pcl_cloud* c, const float* img_hw3_dev, int h, int w, const float* poses_k6_dev, int k,
+                               int num_split_h, int num_split_w, float* hist_intersect_k_dev, void* stream) {
+  if (!hist_intersect_k_dev || k <= 0) { pcl_set_error("bad re-rank arguments"); return PCL_ERR_INVALID; }
+  int rc = pcl_rr_check_split(h, w, num_split_h, num_split_w);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = num_split_h >= 3 ? (num_split_h - 2) * num_split_w : 0;
+  float* rows = nullptr;
+  PCL_CUDA(pcl_pool_alloc((void**)&rows, sizeof(float) * ((size_t)k * 2 * nblk + 64), st));
+  float* ngt = rows + (size_t)k * 2 * nblk;
+  rc = pcl_hist_rerank_blocks(c, img_hw3_dev, h, w, poses_k6_dev, k, num_split_h, num_split_w, rows, ngt, stream);
+  if (rc == PCL_OK) rc = pcl_hist_rerank_finish(rows, ngt, k, num_split_h, num_split_w, hist_intersect_k_dev, stream);
+  pcl_pool_free(rows, st);
+  return rc;
 }

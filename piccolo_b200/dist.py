@@ -61,6 +61,18 @@ def score_sharded(score_fn: Callable[[torch.Tensor], torch.Tensor], poses: torch
     return _all_gather_rows(local, poses.shape[0]).reshape(-1)
 
 
+def rerank_sharded(blocks_fn: Callable[[torch.Tensor], tuple], finish_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor],
+                   poses: torch.Tensor) -> torch.Tensor:
+    """Histogram re-rank with the K candidates sharded: every rank renders and histograms a contiguous slice
+    (blocks_fn: (k,6) -> (rows (k, 2*nblk), ngt (nblk,))), the per-block rows are all-gathered, and every rank replays the
+    reference's candidate loop over ALL rows in order (finish_fn) — its table persists from one candidate to the next
+    (utils.py:547-579), so that part cannot be split.  Returns the (K,) scores on every rank."""
+    rank, ws = world()
+    lo, hi = shard_bounds(poses.shape[0], rank, ws)
+    rows, ngt = blocks_fn(poses[lo:hi])
+    return finish_fn(_all_gather_rows(rows, poses.shape[0]), ngt)
+
+
 def refine_sharded(refine_fn: Callable[[torch.Tensor], torch.Tensor], starts: torch.Tensor) -> torch.Tensor:
     """Candidates are dealt round-robin; each rank refines its own with zero communication, then one
     all-gather of the (loss, pose) rows.  refine_fn maps (b,6) start poses -> (b,7) rows [loss, pose].

@@ -185,6 +185,33 @@ def hist_rerank(cloud: Cloud, img: torch.Tensor, poses: torch.Tensor, num_split_
     return out
 
 
+def hist_rerank_blocks(cloud: Cloud, img: torch.Tensor, poses: torch.Tensor, num_split_h: int = 4, num_split_w: int = 4):
+    """Stage 1 of the re-rank, independent per candidate (pcl_hist_rerank_blocks): returns (rows (K, 2*nblk), ngt (nblk,))."""
+    lib = _lib.load()
+    _require_cuda(img, "img")
+    p = _poses(poses)
+    img_c = _f32c(img)
+    nblk = max(int(num_split_h) - 2, 0) * int(num_split_w)
+    rows = torch.zeros(p.shape[0], 2 * nblk, dtype=torch.float32, device=p.device)
+    ngt = torch.zeros(nblk, dtype=torch.float32, device=p.device)
+    if p.shape[0] > 0:
+        with torch.cuda.device(p.device):
+            _lib.check(lib.pcl_hist_rerank_blocks(cloud._h, img_c.data_ptr(), int(img_c.shape[0]), int(img_c.shape[1]), p.data_ptr(), p.shape[0],
+                                                  int(num_split_h), int(num_split_w), rows.data_ptr(), ngt.data_ptr(), _stream(p.device)))
+    return rows, ngt
+
+
+def hist_rerank_finish(rows: torch.Tensor, ngt: torch.Tensor, num_split_h: int = 4, num_split_w: int = 4) -> torch.Tensor:
+    """Stage 2 over ALL candidates in order (pcl_hist_rerank_finish): (K,) hist_intersect."""
+    lib = _lib.load()
+    _require_cuda(rows, "rows")
+    r, g = _f32c(rows), _f32c(ngt)
+    out = torch.empty(r.shape[0], dtype=torch.float32, device=r.device)
+    with torch.cuda.device(r.device):
+        _lib.check(lib.pcl_hist_rerank_finish(r.data_ptr(), g.data_ptr(), r.shape[0], int(num_split_h), int(num_split_w), out.data_ptr(), _stream(r.device)))
+    return out
+
+
 class Refiner:
     """Fused refinement of B candidates: every iteration is ONE kernel launch doing loss, backward,
     reduction, Adam, ReduceLROnPlateau and the translation clamp (omniloc.py:44-58, :249-269)."""

@@ -106,32 +106,58 @@ def localize_query_host(xyz_h: torch.Tensor, rgb_h: torch.Tensor, img_h: torch.T
     return res[:6], float(res[6])
 
 
-def localize_query_sharded(cloud: engine.Cloud, image: engine.Image, grid: torch.Tensor, cfg, img: torch.Tensor = None, num_split=(4, 4)):
-    """ONE query sharded over the ranks of the default process group (config C3): each rank scores a contiguous
-    slice of the pose grid, the per-pose losses are all-gathered (NCCL, KB-sized), every rank runs the same
-    deterministic top-K / re-rank, the surviving candidates are dealt round-robin for refinement and the
-    (loss, pose) rows are all-gathered before the arg-min.  Cloud and panorama are replicated on every GPU.
+def localize_query_sharded(cloud: engine.Cloud, image: engine.Image, grid: torch.Tensor, cfg, img: torch.Tensor = None, num_split=(4, 4),
+                           refine: str = "points", timers=None):
+    """ONE query sharded over the ranks of the default process group (config C3).  Cloud and panorama are replicated on
+    every GPU.  Every phase shards over its own natural unit:
+      scoring     contiguous slices of the pose grid per rank; the per-pose losses are all-gathered (NCCL, KB-sized) and
+                  every rank runs the same deterministic top-K
+      re-rank     contiguous slices of the K intermediate candidates per rank (render + block histograms), rows all-gathered,
+                  the reference's sequential candidate loop replayed by every rank
+      refinement  refine="points": every rank refines ALL candidates over its share of the POINTS; the per-CTA partial sums
+                  travel as peer stores over NVLink inside the persistent kernel (engine.PeerComm), every rank steps the
+                  same optimiser on the same sums, so no gather is needed and B < #GPUs does not idle GPUs;
+                  refine="candidates": candidates dealt round-robin, one all-gather of the (loss, pose) rows before the arg-min.
     Returns the same dict as `localize_query` on every rank."""
     from . import dist as pdist
+    ev = timers if timers is not None else {}
+
+    def mark(name):
+        if name in ev:
+            ev[name].record()
+
+    mark("score0")
     if isinstance(grid, StartGrid):      # shard the translations: rank slices are whole rows of the loss table
         R = grid.rot.shape[0]
         loss = pdist.score_sharded(lambda tr: engine.score_grid(cloud, image, tr, grid.rot)[0], grid.trans, width=R)
     else:
         loss = pdist.score_sharded(lambda p: engine.score(cloud, image, p)[0], grid)
+    mark("score1")
     if img is not None:
         idx = engine.topk(loss, cfg.num_intermediate)
         mid = grid.index_select(0, idx)
-        keep = engine.topk(-engine.hist_rerank(cloud, img, mid, num_split[0], num_split[1]), cfg.num_input)
+        scores = pdist.rerank_sharded(lambda p: engine.hist_rerank_blocks(cloud, img, p, num_split[0], num_split[1]),
+                                      lambda rows, ngt: engine.hist_rerank_finish(rows, ngt, num_split[0], num_split[1]), mid)
+        keep = engine.topk(-scores, cfg.num_input)
         idx = idx.index_select(0, keep)
     else:
         idx = engine.topk(loss, cfg.num_input)
+    mark("rerank1")
     starts = grid.index_select(0, idx)
-
-    def refine_fn(s):
-        ref = engine.Refiner(s.shape[0], cfg.lr, cfg.factor, cfg.patience, bool(cfg.parallel)).reset(s)
-        out = ref.run(cloud, image, cfg.num_iter).read()
-        return torch.cat([out["loss"].reshape(-1, 1), out["pose"]], dim=1)
-
-    table = pdist.refine_sharded(refine_fn, starts)
+    rank, ws = pdist.world()
+    if refine == "points" and ws > 1 and starts.shape[0] <= 16:
+        ref = engine.Refiner(starts.shape[0], cfg.lr, cfg.factor, cfg.patience, bool(cfg.parallel)).reset(starts)
+        mark("refine0")
+        out = ref.run(cloud, image, cfg.num_iter, comm=pdist.peer_comm()).read()
+        mark("refine1")
+        table = torch.cat([out["loss"].reshape(-1, 1), out["pose"]], dim=1)       # identical on every rank
+    else:
+        def refine_fn(s):
+            r = engine.Refiner(s.shape[0], cfg.lr, cfg.factor, cfg.patience, bool(cfg.parallel)).reset(s)
+            o = r.run(cloud, image, cfg.num_iter).read()
+            return torch.cat([o["loss"].reshape(-1, 1), o["pose"]], dim=1)
+        mark("refine0")
+        table = pdist.refine_sharded(refine_fn, starts)
+        mark("refine1")
     k, pose, best = pdist.argmin_candidate(table)
     return {"pose": pose, "loss": best, "index": k, "candidates": table[:, 1:], "losses": table[:, 0], "start_index": idx, "grid_loss": loss}

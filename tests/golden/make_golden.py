@@ -149,6 +149,7 @@ def make_variants(ref_omniloc, ref_utils, with_c1=True):
     out["rerank_order_f64"] = with_dtype(torch.float64, lambda: rerank(torch.float64))
     print("variants/rerank: top-6", {t: out["rerank_order_" + t][:6].tolist() for t in ("t1", "t8", "f64")})
 
+    np.savez_compressed(os.path.join(HERE, "variants.npz"), **out)
     # ---- (3) the complete C1 query: make_input + six omniloc runs -------------------------------------------------
     if with_c1:
         import importlib.util
@@ -169,11 +170,13 @@ def make_variants(ref_omniloc, ref_utils, with_c1=True):
                     "final_t": np.stack([r[0].detach().numpy().reshape(3) for r in res]).astype(np.float64),
                     "final_R": np.stack([r[1].detach().numpy() for r in res]).astype(np.float64),
                     "final_loss": np.array([float(r[2]) for r in res]), "best": int(np.argmin([float(r[2]) for r in res]))}
-        for tag, fn in (("t4", lambda: with_threads(4, lambda: c1(torch.float32))), ("f64", lambda: with_dtype(torch.float64, lambda: c1(torch.float64)))):
+        # (no fp64 variant here: make_input mixes the cloud with fp32 images inside grid_sample / index_put_, which refuse mixed dtypes)
+        for tag, fn in (("t4", lambda: with_threads(4, lambda: c1(torch.float32))), ("t2", lambda: with_threads(2, lambda: c1(torch.float32)))):
             r = fn()
             for k, v in r.items():
                 out["c1_" + k + "_" + tag] = v
             print("variants/c1", tag, "best", r["best"], "t", r["final_t"][r["best"]], "losses", np.round(r["final_loss"], 4).tolist(), flush=True)
+            np.savez_compressed(os.path.join(HERE, "variants.npz"), **out)
     np.savez_compressed(os.path.join(HERE, "variants.npz"), **out)
 
 

@@ -43,7 +43,16 @@ def _worker(rank, ws, port, q):
         table = pd.refine_sharded(refine_fn, starts)
         k, pose, loss = pd.argmin_candidate(table)
         rows = pd.gather_results(torch.tensor([float(rank), float(loss)]))
-        q.put((rank, full.numpy(), table.numpy(), k, rows.numpy()))
+        # sharded re-rank: per-candidate rows computed on the owning rank, the sequential finish on all rows everywhere
+        cand = poses[:7]                                                        # 7 candidates over 2 ranks: ragged
+
+        def blocks_fn(p):
+            return torch.stack([p[:, 0] * 2 + p[:, 3], p[:, 1] - p[:, 4]], 1), torch.tensor([3.0, 5.0])
+
+        def finish_fn(r, ngt):
+            return torch.cumsum(r[:, 0] * ngt[0] + r[:, 1] * ngt[1], 0)         # order-dependent, like the reference's table
+        rr = pd.rerank_sharded(blocks_fn, finish_fn, cand)
+        q.put((rank, full.numpy(), table.numpy(), k, rows.numpy(), rr.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -69,7 +78,9 @@ def test_sharded_scoring_and_refinement_match_single_process():
     idx = torch.from_numpy(orc.topk_ascending(full.numpy(), 5))
     out = orc.refine_torch(xyz, rgb, img, poses[idx], num_iter=3, factor=0.8)
     table = torch.cat([out["loss"].reshape(-1, 1), out["pose"]], dim=1).numpy()
-    for rank, f, t, k, rows in results:
+    rr_true = torch.cumsum((poses[:7, 0] * 2 + poses[:7, 3]) * 3.0 + (poses[:7, 1] - poses[:7, 4]) * 5.0, 0).numpy()
+    for rank, f, t, k, rows, rr in results:
+        np.testing.assert_allclose(rr, rr_true, rtol=1e-6)
         np.testing.assert_allclose(f, full.numpy(), rtol=1e-6)            # same values on every rank
         np.testing.assert_array_equal(orc.topk_ascending(f, 5), idx.numpy())
         np.testing.assert_allclose(t, table, rtol=1e-4, atol=1e-6)
