@@ -23,7 +23,7 @@ extern std::atomic<long long> g_pcl_launches;
 int pcl_num_sms();
 // process-global tuning knobs (pcl_set_option / PCL_<NAME> in the environment, read once)
 enum { PCL_OPT_PERSIST = 0, PCL_OPT_PDL, PCL_OPT_PB_FWD, PCL_OPT_PB_BWD, PCL_OPT_WAVES, PCL_OPT_SWAP, PCL_OPT_GRID_SWAP, PCL_OPT_SMALL_TABLE,
-       PCL_OPT_RF_NPB, PCL_OPT_RF_DEBUG, PCL_OPT_COUNT };
+       PCL_OPT_RF_NPB, PCL_OPT_RF_DEBUG, PCL_OPT_RF_RES, PCL_OPT_COUNT };
 int pcl_opt(int id);
 
 #define PCL_CUDA(expr)                                                                         \

@@ -131,9 +131,6 @@ static int pcl_refine_run_fused(pcl_refine* r, const pcl_cloud* c, const pcl_ima
   PclRfParams ps;
   memset(&ps, 0, sizeof(ps));
   ps.C = PclCloudView{c->x, c->y, c->z, c->r, c->g, c->b, (long long)c->n};
-  // small batches move their poses every iteration: the compact companion table stays L2-resident (pcl_common.cuh)
-  const PclImage& view = (im->has_small && pcl_opt(PCL_OPT_SMALL_TABLE)) ? im->view_small : im->view;
-  ps.I = view;
   ps.B = r->B;
   pcl_rf_blocks(r->B, &ps.nblk, &ps.npb);
   ps.rank = rank; ps.nranks = nranks;
@@ -147,6 +144,32 @@ static int pcl_refine_run_fused(pcl_refine* r, const pcl_cloud* c, const pcl_ima
   if (G > by_rows) G = by_rows < 1 ? 1 : by_rows;
   if (comm) G = (long long)PCL_RF_CTAS_PER_SM * pcl_num_sms() - 1;                   // every rank must use the same G: the record slots are rank*G + cta
   ps.G = (int)G;
+  bool fully_resident = false;
+  {
+    // points a CTA keeps in shared memory for the whole run: its whole range when that fits beside the kernel's static
+    // arrays (<= ~8.6 k points per CTA = 1.27 M points per GPU), whole 2048-point groups of it for clouds up to 3x that
+    // size, nothing beyond (the resident share is small there and the texel gather makes better use of the unified
+    // shared-memory/L1 array).  Option RF_RES: -1/1 = this rule, 0 = off.
+    int dev = 0, optin = 0;
+    PCL_CUDA(cudaGetDevice(&dev));
+    PCL_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    // keep >= 60 KB of the 256 KB array as L1 for the texel gather: 28 KB (the next carve-out step) was measured slower
+    // than not keeping the points at all
+    const long long budget = (long long)(optin < 196 * 1024 ? optin : 196 * 1024) - PCL_RF_SMEM_STATIC;
+    const long long cap = budget / 24 / 32 * 32;
+    const long long per_cta = (n_pts + G - 1) / G;
+    long long res = per_cta <= cap ? per_cta : (per_cta <= 3 * cap ? cap / PCL_RF_GROUP * PCL_RF_GROUP : 0);
+    if (pcl_opt(PCL_OPT_RF_RES) == 0 || cap <= 0) res = 0;
+    fully_resident = res > 0 && res >= per_cta;
+    ps.res_pts = (int)res;
+  }
+  // Texel table.  The poses of a small batch move every iteration, so the gather lands at unpredictable places of the
+  // table: it has to stay in L2.  When the cloud streams through L2 as well, only the compact companion table (U8Q,
+  // 16 B per footprint) survives next to it; when the points are resident in shared memory the cloud leaves L2 to the
+  // table and the fp16-basis table (F16D: no unpacking, 161 instead of 175 instructions per evaluation) is the faster one
+  // (C2: 38.7 vs 40.9 us per iteration).  Option SMALL_TABLE: 1 = this rule, 0 = always the main table, 2 = always the companion.
+  const PclImage& view = (im->has_small && pcl_opt(PCL_OPT_SMALL_TABLE) && !(fully_resident && pcl_opt(PCL_OPT_SMALL_TABLE) != 2)) ? im->view_small : im->view;
+  ps.I = view;
   ps.num_iter = num_iter;
   ps.state = r->state; ps.evalp = r->evalp; ps.loss = r->loss;
   ps.box = c->lo_hi_dev;

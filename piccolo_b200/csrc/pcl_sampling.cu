@@ -294,8 +294,8 @@ struct PclLaunchPlan { int PB, gx, gy, NS; long long n_rows; };
 
 // Tuning knobs (A/B experiments and tests): process-global, read ONCE from the environment (PCL_<NAME>) on first use,
 // changed afterwards only through pcl_set_option — no getenv on the launch path.
-static const char* const g_opt_names[PCL_OPT_COUNT] = {"PERSIST", "PDL", "PB_FWD", "PB_BWD", "WAVES", "SWAP", "GRID_SWAP", "SMALL_TABLE", "RF_NPB", "RF_DEBUG"};
-static const int g_opt_defaults[PCL_OPT_COUNT] = {1, 1, 0, 0, 0, 1, 1, 1, 0, 0};
+static const char* const g_opt_names[PCL_OPT_COUNT] = {"PERSIST", "PDL", "PB_FWD", "PB_BWD", "WAVES", "SWAP", "GRID_SWAP", "SMALL_TABLE", "RF_NPB", "RF_DEBUG", "RF_RES"};
+static const int g_opt_defaults[PCL_OPT_COUNT] = {1, 1, 0, 0, 0, 1, 1, 1, 0, 0, 1};
 static std::atomic<int> g_opt[PCL_OPT_COUNT];
 static std::once_flag g_opt_once;
 
