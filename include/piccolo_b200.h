@@ -179,9 +179,9 @@ int pcl_refine_run_sharded(pcl_refine* r, const pcl_cloud* c, const pcl_image* i
  * lr_b_dev (nullable, double): current learning rates */
 int pcl_refine_read(const pcl_refine* r, float* pose_b6_dev, float* param_b6_dev, float* loss_b_dev,
                     double* lr_b_dev, void* stream);
-/* Diagnostics (option RF_DEBUG=1 before the run): cycle counters of the last persistent run per compute CTA:
- * out_host[cta*2 + 0] = cycles inside phases, [cta*2 + 1] = cycles waiting for the next poses.  Returns the number of
- * compute CTAs recorded (0: nothing recorded) or a negative pcl_status; blocks on `stream`. */
+/* Diagnostics (option RF_DEBUG=1 before the run): counters of the last persistent run, 4 per CTA (out_host[cta*4 + k]):
+ * compute CTAs (warp 0) {cycles inside phases, cycles waiting for the next poses, phases whose poses were prefetched, 0}; the LAST row is the service CTA {cycles waiting for records, cycles reducing and stepping}.
+ * Returns the number of rows recorded (0: nothing recorded) or a negative pcl_status; blocks on `stream`. */
 int pcl_refine_debug_stats(const pcl_refine* r, unsigned long long* out_host, int max_ctas, void* stream);
 void pcl_refine_destroy(pcl_refine* r);
 

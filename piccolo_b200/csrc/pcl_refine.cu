@@ -213,9 +213,9 @@ static int pcl_refine_run_fused(pcl_refine* r, const pcl_cloud* c, const pcl_ima
       PCL_CUDA(e);
       ps.bc = r->bc_dev;
       if (pcl_opt(PCL_OPT_RF_DEBUG)) {
-        rc = pcl_rf_grow((void**)&r->dbg, &r->dbg_cap, (size_t)G * 2, sizeof(unsigned long long), st);
+        rc = pcl_rf_grow((void**)&r->dbg, &r->dbg_cap, (size_t)(G + 1) * 4, sizeof(unsigned long long), st);
         if (rc) return rc;
-        ps.dbg = r->dbg; r->dbg_ctas = (int)G;
+        ps.dbg = r->dbg; r->dbg_ctas = (int)G + 1;
       }
       e = pcl_rf_dispatch_persistent(view.fmt, ps, st);
       if (e == cudaSuccess) {
@@ -284,13 +284,14 @@ extern "C" int pcl_refine_read(const pcl_refine* r, float* pose_b6_dev, float* p
   return PCL_OK;
 }
 
-// Option RF_DEBUG: cycle counters of the last persistent run, out[cta*2 + {0: in phases, 1: waiting for poses}].
-// Returns the number of compute CTAs (0 when nothing was recorded).  Blocks on `stream`.
+// Option RF_DEBUG: counters of the last persistent run, 4 per CTA: compute CTAs {cycles of warp 0 in phases, cycles waiting
+// for poses, phases whose poses were already there, 0}; the last row is the service CTA {cycles
+// waiting for records, cycles reducing + stepping, 0, 0}.  Returns the number of rows (0 when nothing was recorded).  Blocks on `stream`.
 extern "C" int pcl_refine_debug_stats(const pcl_refine* r, unsigned long long* out_host, int max_ctas, void* stream) {
   if (!r || !out_host) { pcl_set_error("null refine handle or output"); return PCL_ERR_INVALID; }
   if (!r->dbg || r->dbg_ctas <= 0) return 0;
   const int n = r->dbg_ctas < max_ctas ? r->dbg_ctas : max_ctas;
-  PCL_CUDA(cudaMemcpyAsync(out_host, r->dbg, sizeof(unsigned long long) * 2 * (size_t)n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  PCL_CUDA(cudaMemcpyAsync(out_host, r->dbg, sizeof(unsigned long long) * 4 * (size_t)n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   PCL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return n;
 }

@@ -47,7 +47,7 @@ struct PclRfParams {
   int G;                        // CTAs per rank
   int res_pts;                  // points of a CTA's range kept resident in shared memory (whole 2048-point groups, or the whole range); 0 = none
   int rank, nranks;
-  unsigned long long* dbg;      // nullable: per compute CTA {cycles in phases, cycles waiting for poses} (option RF_DEBUG)
+  unsigned long long* dbg;      // nullable: 4 counters per CTA, see pcl_refine_debug_stats (option RF_DEBUG)
   double* rec[PCL_RF_MAXRANKS];           // record buffers of all ranks (rec[rank] is local): [2][nblk][nranks*G][MAXNPB*8]
   unsigned int* arrive[PCL_RF_MAXRANKS];  // arrival counters of all ranks: [nblk], monotonic
   unsigned int arrive_base[PCL_RF_MAXBLK];   // value of block b's counter when this run starts
@@ -200,8 +200,10 @@ __device__ __forceinline__ void pcl_rf_phase(const PclCloudView& C, const PclIma
   const int r = (int)(c_end - rem0);
   const bool rem_res = (long long)res_n >= c_end - c_begin;      // the whole range is resident
   if (r > 0) {
-    const int S = PCL_RF_THREADS / np;
-    const int p_t = tid % np, slot = tid / np;
+    // tid / np and THREADS / np for np <= 4 by multiply-shift (exact for tid <= 65535 / 4)
+    const unsigned int inv = np == 1 ? 65536u : np == 2 ? 32768u : np == 3 ? 21846u : 16384u;
+    const int S = (int)(((unsigned int)PCL_RF_THREADS * inv) >> 16);
+    const int slot = (int)(((unsigned int)tid * inv) >> 16), p_t = tid - slot * np;
     PclAcc ar;
     pcl_rf_zero(ar);
     if (slot < S) {
@@ -372,11 +374,14 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
       pcl_pose_from_params(s_evalp[tid], s_pose[0][tid]);
     }
     __syncthreads();
+    long long sv_wait = 0, sv_work = 0;
     for (int it = 0; it < ps.num_iter; ++it) {
       for (int b = 0; b < ps.nblk; ++b) {
         const int p0 = b * ps.npb, np = min(ps.npb, ps.B - p0);
+        const long long s0 = ps.dbg ? clock64() : 0;
         if (tid == 0) pcl_rf_spin(ps.arrive[ps.rank] + b, ps.arrive_base[b] + (unsigned int)(it + 1) * (unsigned int)n_rec, ps.nranks > 1, 32u);
         __syncthreads();
+        const long long s1 = ps.dbg ? clock64() : 0;
         // records are double-buffered by iteration parity: a fast rank's next record must not overwrite the copy a slower
         // rank's service CTA is still reading
         pcl_rf_finalize(ps.rec[ps.rank] + ((size_t)((ps.parity0 + it) & 1) * ps.nblk + b) * rec_blk, n_rec, np, s_sum, s_state + p0, &s_evalp[p0][0], &s_pose[0][p0], ps.I, k,
@@ -386,9 +391,11 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
         if (tid == 0) {                                            // release is cumulative over the barrier above; no fence:
           const unsigned int v = ps.ready_base[b] + (unsigned int)(it + 1);   // a gpu-scope fence would also invalidate this SM's L1
           asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ps.ready + b), "r"(v) : "memory");
+          if (ps.dbg) { sv_wait += s1 - s0; sv_work += clock64() - s1; }
         }
       }
     }
+    if (ps.dbg && tid == 0) { ps.dbg[4 * (size_t)G] = (unsigned long long)sv_wait; ps.dbg[4 * (size_t)G + 1] = (unsigned long long)sv_work; ps.dbg[4 * (size_t)G + 2] = 0; ps.dbg[4 * (size_t)G + 3] = 0; }
     if (tid < ps.B) {                                            // the end state
       ps.state[tid] = s_state[tid];
 #pragma unroll
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
   __syncthreads();
 
   int ph = 0;
-  long long t_busy = 0, t_wait = 0;
+  long long t_busy = 0, t_wait = 0, n_hit = 0;
   for (int it = 0; it < ps.num_iter; ++it) {
     for (int b = 0; b < ps.nblk; ++b, ++ph) {
       const int buf = ph & 1;
@@ -426,7 +433,9 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
       if (it == 0) {
         if (tid < np) pcl_pose_from_params(ps.evalp + 6 * (size_t)(p0 + tid), s_pose[buf][tid]);
         __syncthreads();
-      } else if (s_pref[buf] != ph) {                            // not prefetched (uniform: written before the last barrier)
+      } else if (s_pref[buf] == ph) {
+        n_hit += 1;
+      } else {                                                   // not prefetched (uniform: written before the last barrier)
         if (tid == 0) pcl_rf_spin(ps.ready + b, ps.ready_base[b] + (unsigned int)it, false, 0u);
         __syncthreads();
         if (tid < np * 12) reinterpret_cast<float*>(&s_pose[buf][0])[tid] = __ldcg(ps.posebuf + (size_t)p0 * 12 + tid);
@@ -464,7 +473,10 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
       }
     }
   }
-  if (ps.dbg && tid == 0) { ps.dbg[2 * (size_t)cta] = (unsigned long long)t_busy; ps.dbg[2 * (size_t)cta + 1] = (unsigned long long)t_wait; }
+  if (ps.dbg && tid == 0) {
+    ps.dbg[4 * (size_t)cta] = (unsigned long long)t_busy; ps.dbg[4 * (size_t)cta + 1] = (unsigned long long)t_wait;
+    ps.dbg[4 * (size_t)cta + 2] = (unsigned long long)n_hit; ps.dbg[4 * (size_t)cta + 3] = 0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

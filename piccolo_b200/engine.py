@@ -243,9 +243,10 @@ class Refiner:
         return self
 
     def debug_stats(self):
-        """Option RF_DEBUG: (ctas, 2) uint64 numpy array {cycles in phases, cycles waiting for poses} of the last persistent run."""
+        """Option RF_DEBUG: (ctas + 1, 4) uint64 numpy array of the last persistent run: compute CTAs {cycles in phases, cycles
+        waiting for poses, phases with prefetched poses, 0}, last row = service CTA {waiting, working}."""
         import numpy as np
-        buf = np.zeros((512, 2), dtype=np.uint64)
+        buf = np.zeros((512, 4), dtype=np.uint64)
         with torch.cuda.device(self.device):
             n = _lib.load().pcl_refine_debug_stats(self._h, buf.ctypes.data, 512, _stream(self.device))
         if n < 0:
