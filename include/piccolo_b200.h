@@ -82,8 +82,11 @@ int pcl_set_option(const char* name, int value);
 
 /* ---- coloured point cloud ------------------------------------------------------------------ */
 /* xyz_n3_dev, rgb_n3_dev: (N,3) float32.  q: out_of_room_quantile (clamp box = order statistics
- * int(N*q) and int(N*(1-q)) per axis, utils.py:222-227).  Asynchronous: all work is ordered on `stream`; destroy the
- * handle only when no work using it is in flight on other streams. */
+ * int(N*q) and int(N*(1-q)) per axis, utils.py:222-227).  Asynchronous: all work is ordered on `stream`, and the
+ * storage is freed in stream order there.  Compute entries may use the handle on another stream once that stream is
+ * ordered after the creation (event / stream wait): every entry records its use, and pcl_cloud_destroy /
+ * pcl_image_destroy make the creation stream wait for the most recent record before the storage returns to the pool
+ * (uses on several foreign streams: order the earlier ones before the last one yourself). */
 int pcl_cloud_create(const float* xyz_n3_dev, const float* rgb_n3_dev, int64_t n, double q, int order,
                      void* stream, pcl_cloud** out);
 int64_t pcl_cloud_size(const pcl_cloud* c);

@@ -41,8 +41,18 @@ int pcl_opt(int id);
     PCL_CUDA(cudaGetLastError());               \
   } while (0)
 
+// Handles are built and freed in stream order on their creation stream (`owner`).  Compute entries may run on any other
+// stream: each records its last use there (PclUseGuard), and the destroy makes the owner stream wait for that record
+// before the storage goes back to the pool.  (One record per handle: with several foreign streams the most recent one
+// is waited for; order the others after it yourself.)
+struct PclUse {
+  cudaEvent_t ev;
+  int cross;                    // 1: used on a stream other than the owner since creation
+};
+
 struct pcl_cloud {
   cudaStream_t owner;           // stream the storage is ordered on (freed there)
+  PclUse use;
   float* block;                 // one allocation: x|y|z|r|g|b, each n_pad floats
   float *x, *y, *z, *r, *g, *b;
   int64_t n, n_pad;
@@ -54,6 +64,7 @@ struct pcl_cloud {
 
 struct pcl_image {
   cudaStream_t owner;
+  PclUse use;
   void* data;
   size_t bytes;
   PclImage view;                // view.data == data
@@ -120,6 +131,31 @@ struct pcl_comm {
   char* peer[PCL_COMM_MAXRANKS];        // peer[rank] is the local window
   unsigned int bar_epoch, ag_epoch;     // host copies of the monotonic counters (identical call sequences on all ranks)
   unsigned int arrive_base[8];
+};
+
+static inline void pcl_note_use(cudaStream_t owner, const PclUse* use_, cudaStream_t st) {
+  if (st == owner) return;
+  PclUse* u = const_cast<PclUse*>(use_);
+  if (!u->ev && cudaEventCreateWithFlags(&u->ev, cudaEventDisableTiming) != cudaSuccess) { u->ev = nullptr; return; }
+  if (cudaEventRecord(u->ev, st) == cudaSuccess) u->cross = 1;
+}
+// before freeing a handle's storage on its owner stream
+static inline void pcl_use_release(cudaStream_t owner, PclUse* u) {
+  if (u->ev) {
+    if (u->cross) cudaStreamWaitEvent(owner, u->ev, 0);
+    cudaEventDestroy(u->ev);
+    u->ev = nullptr;
+  }
+}
+// declared at the top of a compute entry: records the use when the entry returns (after everything is enqueued)
+struct PclUseGuard {
+  const pcl_cloud* c;
+  const pcl_image* im;
+  cudaStream_t st;
+  ~PclUseGuard() {
+    if (c) pcl_note_use(c->owner, &c->use, st);
+    if (im) pcl_note_use(im->owner, &im->use, st);
+  }
 };
 
 struct PclCloudView {

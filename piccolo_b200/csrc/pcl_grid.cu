@@ -241,6 +241,7 @@ extern "C" int pcl_score_grid(const pcl_cloud* c, const pcl_image* im, const flo
     return PCL_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  PclUseGuard guard{c, im, st};
   if (r > PCL_GRID_MAX_ROT) {
     float* poses = nullptr;
     const long long P = (long long)t * r;

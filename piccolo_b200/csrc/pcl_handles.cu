@@ -166,6 +166,7 @@ extern "C" int pcl_cloud_bounds(const pcl_cloud* c, float* lo_hi) {
 
 extern "C" void pcl_cloud_destroy(pcl_cloud* c) {
   if (!c) return;
+  pcl_use_release(c->owner, &c->use);
   if (c->block) pcl_pool_free(c->block, c->owner);
   free(c);
 }
@@ -350,6 +351,7 @@ extern "C" int pcl_image_format(const pcl_image* im) { return im ? im->view.fmt 
 
 extern "C" void pcl_image_destroy(pcl_image* im) {
   if (!im) return;
+  pcl_use_release(im->owner, &im->use);
   if (im->view.fmt == PCL_FMT_TEX) {
     if (im->view.tex) cudaDestroyTextureObject((cudaTextureObject_t)im->view.tex);
     if (im->data) cudaFreeArray((cudaArray_t)im->data);

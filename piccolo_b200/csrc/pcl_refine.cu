@@ -259,6 +259,7 @@ static int pcl_refine_check(pcl_refine* r, const pcl_cloud* c, const pcl_image* 
 extern "C" int pcl_refine_run(pcl_refine* r, const pcl_cloud* c, const pcl_image* im, int num_iter, void* stream) {
   int rc = pcl_refine_check(r, c, im, num_iter);
   if (rc) return rc;
+  PclUseGuard guard{c, im, (cudaStream_t)stream};
   if (r->B <= PCL_RF_MAXB) return pcl_refine_run_fused(r, c, im, num_iter, nullptr, (cudaStream_t)stream);
   return pcl_generic_refine_iters(r, c, im, num_iter, (cudaStream_t)stream);
 }
@@ -266,6 +267,7 @@ extern "C" int pcl_refine_run(pcl_refine* r, const pcl_cloud* c, const pcl_image
 extern "C" int pcl_refine_run_sharded(pcl_refine* r, const pcl_cloud* c, const pcl_image* im, int num_iter, pcl_comm* comm, void* stream) {
   int rc = pcl_refine_check(r, c, im, num_iter);
   if (rc) return rc;
+  PclUseGuard guard{c, im, (cudaStream_t)stream};
   if (!comm || !comm->connected) { pcl_set_error("pcl_comm is null or not connected"); return PCL_ERR_INVALID; }
   if (r->B > PCL_RF_MAXB) { pcl_set_error("the point-sharded refinement handles up to %d candidates", PCL_RF_MAXB); return PCL_ERR_INVALID; }
   if (comm->nranks == 1) return pcl_refine_run_fused(r, c, im, num_iter, nullptr, (cudaStream_t)stream);

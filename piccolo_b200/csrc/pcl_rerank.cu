@@ -33,33 +33,53 @@ __device__ __forceinline__ int pcl_rr_bin(float r, float g, float b) {
   return br + 8 * bg + 64 * bb;
 }
 
-// rows [ky_lo, ky_hi) of the key image are kept: the compared row blocks plus one source row above and below
-__global__ void pcl_rr_splat_kernel(const PclCloudView C, const PclPose* __restrict__ poses, const int H, const int W,
-                                    const int ky_lo, const int ky_hi, unsigned long long* __restrict__ keys) {
+// rows [ky_lo, ky_hi) of the key image are kept: the compared row blocks plus one source row above and below.
+// One thread per POINT, looping over the candidates (poses in shared memory): the point, its colour bin and its lit flag
+// are loaded / formed once instead of once per candidate (round 2: 210 -> 128 instructions per point·candidate).
+#define PCL_RR_POSE_CHUNK 64
+__global__ void __launch_bounds__(256) pcl_rr_splat_kernel(const PclCloudView C, const PclPose* __restrict__ poses, const int K, const int H, const int W,
+                                                           const int ky_lo, const int ky_hi, unsigned long long* __restrict__ keys) {
+  __shared__ PclPose s_pose[PCL_RR_POSE_CHUNK];
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= C.n) return;
-  const PclPose P = poses[blockIdx.y];
-  const float dx = C.x[i] - P.tx, dy = C.y[i] - P.ty, dz = C.z[i] - P.tz;
-  const float qx = P.r00 * dx + P.r01 * dy + P.r02 * dz;
-  const float qy = P.r10 * dx + P.r11 * dy + P.r12 * dz;
-  const float qz = P.r20 * dx + P.r21 * dy + P.r22 * dz;
-  // cloud2idx, fp32 op for op (utils.py:44-59) with the kernels' minimax atan2 (1e-7 rad: moves a point across a
-  // pixel-truncation boundary with probability ~1e-5), then make_pano's pixel truncation (utils.py:159-165).
-  // Rows first: points whose centre row is outside the kept band stop here.
-  const float theta = pcl_atan2_pos(sqrtf(qx * qx + qy * qy), qz + 1e-6f);
-  const float v = 2.0f * (theta / 3.14159265358979323846f) - 1.0f;
-  const int y = (int)(((v + 1.0f) / 2.0f) * (float)(H - 1));
-  if (y < ky_lo || y >= ky_hi) return;
-  const float phi = pcl_atan2(qy, qx + 1e-6f) + 3.14159265358979323846f;
-  const float u = 2.0f * (1.0f - phi / 6.28318530717958647692f) - 1.0f;
-  const int x = (int)(((u + 1.0f) / 2.0f) * (float)(W - 1));
-  const float dist = sqrtf(qx * qx + qy * qy + qz * qz);
-  const float r = C.r[i], g = C.g[i], b = C.b[i];
-  const unsigned int lit = !(r * 255.0f == 0.0f && g * 255.0f == 0.0f && b * 255.0f == 0.0f);       // proj_mask (utils.py:554)
-  const unsigned long long key = PCL_RR_PRESENT | ((unsigned long long)(~__float_as_uint(dist)) << PCL_RR_LOW_BITS) |
-                                 (unsigned long long)((lit << 9) | (unsigned int)pcl_rr_bin(r, g, b));
-  unsigned long long* cell = keys + ((size_t)blockIdx.y * (size_t)(ky_hi - ky_lo) + (size_t)(y - ky_lo)) * (size_t)W + (size_t)x;
-  if (__ldcg(cell) < key) atomicMax(cell, key);      // a stale read only costs a redundant atomic, never a wrong result
+  const bool live = i < C.n;
+  float px = 0.f, py = 0.f, pz = 0.f;
+  unsigned long long low = 0ull;
+  if (live) {
+    px = C.x[i]; py = C.y[i]; pz = C.z[i];
+    const float r = C.r[i], g = C.g[i], b = C.b[i];
+    const unsigned int lit = !(r * 255.0f == 0.0f && g * 255.0f == 0.0f && b * 255.0f == 0.0f);       // proj_mask (utils.py:554)
+    low = (unsigned long long)((lit << 9) | (unsigned int)pcl_rr_bin(r, g, b));
+  }
+  const size_t cand_stride = (size_t)(ky_hi - ky_lo) * (size_t)W;
+  for (int k0 = 0; k0 < K; k0 += PCL_RR_POSE_CHUNK) {
+    const int kn = min(PCL_RR_POSE_CHUNK, K - k0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < kn * 12; j += blockDim.x) reinterpret_cast<float*>(s_pose)[j] = reinterpret_cast<const float*>(poses + k0)[j];
+    __syncthreads();
+    if (!live) continue;
+#pragma unroll 2
+    for (int k = 0; k < kn; ++k) {
+      const PclPose P = s_pose[k];
+      const float dx = px - P.tx, dy = py - P.ty, dz = pz - P.tz;
+      const float qx = P.r00 * dx + P.r01 * dy + P.r02 * dz;
+      const float qy = P.r10 * dx + P.r11 * dy + P.r12 * dz;
+      const float qz = P.r20 * dx + P.r21 * dy + P.r22 * dz;
+      // cloud2idx, fp32 op for op (utils.py:44-59) with the kernels' minimax atan2 (1e-7 rad: moves a point across a
+      // pixel-truncation boundary with probability ~1e-5), then make_pano's pixel truncation (utils.py:159-165).
+      // Rows first: points whose centre row is outside the kept band stop here.
+      const float theta = pcl_atan2_pos(sqrtf(qx * qx + qy * qy), qz + 1e-6f);
+      const float v = 2.0f * (theta / 3.14159265358979323846f) - 1.0f;
+      const int y = (int)(((v + 1.0f) / 2.0f) * (float)(H - 1));
+      if (y < ky_lo || y >= ky_hi) continue;
+      const float phi = pcl_atan2(qy, qx + 1e-6f) + 3.14159265358979323846f;
+      const float u = 2.0f * (1.0f - phi / 6.28318530717958647692f) - 1.0f;
+      const int x = (int)(((u + 1.0f) / 2.0f) * (float)(W - 1));
+      const float dist = sqrtf(qx * qx + qy * qy + qz * qz);
+      const unsigned long long key = PCL_RR_PRESENT | ((unsigned long long)(~__float_as_uint(dist)) << PCL_RR_LOW_BITS) | low;
+      unsigned long long* cell = keys + (size_t)(k0 + k) * cand_stride + (size_t)(y - ky_lo) * (size_t)W + (size_t)x;
+      if (__ldcg(cell) < key) atomicMax(cell, key);      // a stale read only costs a redundant atomic, never a wrong result
+    }
+  }
 }
 
 // The point make_pano leaves in pixel (y, x): offsets in REVERSE call order (utils.py:190-198: idx8, 7, ..., 1, centre;
@@ -130,48 +150,65 @@ __global__ void pcl_rr_img_hist_kernel(const float* __restrict__ img, const int 
   if (threadIdx.x == 0 && total) atomicAdd(&n_gt[blk], total);
 }
 
-// candidate side: one CTA per (block, candidate)
-__global__ void pcl_rr_cand_hist_kernel(const PclCloudView C, const float* __restrict__ img, const unsigned long long* __restrict__ keys,
-                                        const int H, const int W, const int nsh, const int nsw, const int ky_lo, const int ky_hi,
-                                        const unsigned int* __restrict__ img_hist, const unsigned int* __restrict__ n_gt,
-                                        float* __restrict__ rows /*[K][2*nblk]: intersection per block, then lit-pixel count per block*/) {
+// candidate side, pass 1: raw 512-bin histogram counts of the rendered pixels per (candidate, compared block).  A CTA
+// takes a strip of PCL_RR_STRIP rows of one block (K x nblk x bh/STRIP CTAs: no tail wave, no long per-thread loops),
+// counts in shared memory and adds its non-empty bins to the block's histogram in global memory.
+#define PCL_RR_STRIP 32
+__global__ void __launch_bounds__(256) pcl_rr_cand_hist_kernel(const float* __restrict__ img, const unsigned long long* __restrict__ keys,
+                                                               const int H, const int W, const int nsh, const int nsw, const int ky_lo, const int ky_hi,
+                                                               unsigned int* __restrict__ cand_hist /*[K][nblk][512]*/) {
   __shared__ unsigned int hist[512];
-  __shared__ unsigned int s_total[32];
-  __shared__ float red[32];
-  const int blk = blockIdx.x, cand = blockIdx.y, nblk = gridDim.x, bh = H / nsh, bw = W / nsw;
+  const int nblk = (nsh - 2) * nsw, bh = H / nsh, bw = W / nsw;
+  const int strips = (bh + PCL_RR_STRIP - 1) / PCL_RR_STRIP;
+  const int blk = blockIdx.x / strips, strip = blockIdx.x - blk * strips, cand = blockIdx.y;
   const int h = 1 + blk / nsw, w = blk % nsw;
   for (int i = threadIdx.x; i < 512; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   const unsigned long long* kimg = keys + (size_t)cand * (size_t)(ky_hi - ky_lo) * (size_t)W;
-#pragma unroll 2
-  for (int p = threadIdx.x; p < bh * bw; p += blockDim.x) {
-    const int y = h * bh + p / bw, x = w * bw + p % bw;
-    const float* px = img + ((size_t)y * W + x) * 3;
-    const float i0 = px[0], i1 = px[1], i2 = px[2];            // independent of the keys: in flight together with them
-    const unsigned long long key = pcl_rr_winner(kimg, H, W, ky_lo, y, x);
-    const bool img_lit = !(i0 * 255.0f == 0.0f && i1 * 255.0f == 0.0f && i2 * 255.0f == 0.0f);       // img_mask
-    if (key != 0ull && img_lit && ((key >> 9) & 1ull)) atomicAdd(&hist[(unsigned int)key & 511u], 1u);
+  const int y0 = h * bh + strip * PCL_RR_STRIP, y1 = min(y0 + PCL_RR_STRIP, (h + 1) * bh);
+  for (int y = y0; y < y1; ++y) {
+    for (int xo = threadIdx.x; xo < bw; xo += blockDim.x) {
+      const int x = w * bw + xo;
+      const float* px = img + ((size_t)y * W + x) * 3;
+      const float i0 = px[0], i1 = px[1], i2 = px[2];            // independent of the keys: in flight together with them
+      const unsigned long long key = pcl_rr_winner(kimg, H, W, ky_lo, y, x);
+      const bool img_lit = !(i0 * 255.0f == 0.0f && i1 * 255.0f == 0.0f && i2 * 255.0f == 0.0f);       // img_mask
+      if (key != 0ull && img_lit && ((key >> 9) & 1ull)) atomicAdd(&hist[(unsigned int)key & 511u], 1u);
+    }
   }
   __syncthreads();
-  // number of lit rendered pixels of the block = sum of the histogram
-  unsigned int cnt = 0;
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) cnt += hist[i];
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0) s_total[threadIdx.x >> 5] = cnt;
-  __syncthreads();
-  unsigned int total = 0;
-  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) total += s_total[i];
-  float s = 0.0f;
-  const float tot = (float)total, gtot = (float)n_gt[blk];      // hist / hist.sum() on both sides (color_utils.py:103)
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) s += fminf((float)img_hist[blk * 512 + i] / gtot, (float)hist[i] / tot);
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  unsigned int* out = cand_hist + ((size_t)cand * nblk + blk) * 512;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) if (hist[i]) atomicAdd(out + i, hist[i]);
+}
+
+// pass 2: one warp per (candidate, block): lit-pixel count = sum of the histogram, intersection with the query's
+// normalised histogram (hist / hist.sum() on both sides, color_utils.py:103)
+__global__ void pcl_rr_intersect_kernel(const unsigned int* __restrict__ cand_hist, const unsigned int* __restrict__ img_hist,
+                                        const unsigned int* __restrict__ n_gt, const int nblk, const int K,
+                                        float* __restrict__ rows /*[K][2*nblk]: intersection per block, then lit-pixel count per block*/) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= K * nblk) return;
+  const int cand = wid / nblk, blk = wid - cand * nblk;
+  const unsigned int* hc = cand_hist + (size_t)wid * 512;
+  unsigned int cnt[16], total = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { cnt[j] = hc[lane + 32 * j]; total += cnt[j]; }
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  const float tot = (float)total, gtot = (float)n_gt[blk];
+  // summation order of the round-1 kernel (512 threads: thread i owned bin i, warp sums, then the 16 warp sums in order)
+  float ws[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float s = fminf((float)img_hist[blk * 512 + lane + 32 * j] / gtot, (float)cnt[j] / tot);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    ws[j] = s;
+  }
+  if (lane == 0) {
     float t = 0.0f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t += ws[j];
     rows[(size_t)cand * 2 * nblk + blk] = t;
-    rows[(size_t)cand * 2 * nblk + nblk + blk] = (float)total;       // exact: a block has < 2^24 pixels
+    rows[(size_t)cand * 2 * nblk + nblk + blk] = tot;            // exact: a block has < 2^24 pixels
   }
 }
 
@@ -230,6 +267,7 @@ extern "C" int pcl_hist_rerank_blocks(const pcl_cloud* c, const float* img_hw3_d
   if (rc) return rc;
   if (num_split_h < 3) return PCL_OK;                     // no compared row blocks (utils.py:548: range(1, nsh-1) is empty): nothing to compute
   cudaStream_t st = (cudaStream_t)stream;
+  PclUseGuard guard{c, nullptr, st};
   const int bh = h / num_split_h, nblk = (num_split_h - 2) * num_split_w;
   const int y_lo = bh, y_hi = (num_split_h - 1) * bh;
   const int ky_lo = y_lo - 1, ky_hi = y_hi + 1 < h ? y_hi + 1 : h;       // one source row above and below the compared band
@@ -237,7 +275,8 @@ extern "C" int pcl_hist_rerank_blocks(const pcl_cloud* c, const float* img_hw3_d
   const size_t off_pose = (key_bytes + 255) & ~(size_t)255;
   const size_t off_ih = off_pose + (((size_t)k * sizeof(PclPose) + 255) & ~(size_t)255);
   const size_t off_ngt = off_ih + (size_t)nblk * 512 * sizeof(unsigned int);
-  const size_t total = off_ngt + (((size_t)nblk * sizeof(int) + 255) & ~(size_t)255);
+  const size_t off_ch = off_ngt + (((size_t)nblk * sizeof(int) + 255) & ~(size_t)255);
+  const size_t total = off_ch + (size_t)k * nblk * 512 * sizeof(unsigned int);
   char* buf;
   PCL_CUDA(pcl_pool_alloc((void**)&buf, total, st));
   cudaError_t e = cudaMemsetAsync(buf, 0, key_bytes, st);
@@ -247,13 +286,16 @@ extern "C" int pcl_hist_rerank_blocks(const pcl_cloud* c, const float* img_hw3_d
   PclPose* poses = (PclPose*)(buf + off_pose);
   unsigned int* img_hist = (unsigned int*)(buf + off_ih);
   unsigned int* n_gt = (unsigned int*)(buf + off_ngt);
+  unsigned int* cand_hist = (unsigned int*)(buf + off_ch);
   PclCloudView C = {c->x, c->y, c->z, c->r, c->g, c->b, (long long)c->n};
   pcl_rr_pose_kernel<<<(k + 63) / 64, 64, 0, st>>>(poses_k6_dev, k, poses);
-  pcl_rr_splat_kernel<<<dim3((unsigned int)((c->n + 255) / 256), k), 256, 0, st>>>(C, poses, h, w, ky_lo, ky_hi, keys);
+  pcl_rr_splat_kernel<<<(unsigned int)((c->n + 255) / 256), 256, 0, st>>>(C, poses, k, h, w, ky_lo, ky_hi, keys);
   pcl_rr_img_hist_kernel<<<dim3(nblk, 32), 256, 0, st>>>(img_hw3_dev, h, w, num_split_h, num_split_w, img_hist, n_gt);
-  pcl_rr_cand_hist_kernel<<<dim3(nblk, k), 512, 0, st>>>(C, img_hw3_dev, keys, h, w, num_split_h, num_split_w, ky_lo, ky_hi, img_hist, n_gt, rows_k_dev);
+  const int strips = (bh + PCL_RR_STRIP - 1) / PCL_RR_STRIP;
+  pcl_rr_cand_hist_kernel<<<dim3(nblk * strips, k), 256, 0, st>>>(img_hw3_dev, keys, h, w, num_split_h, num_split_w, ky_lo, ky_hi, cand_hist);
+  pcl_rr_intersect_kernel<<<(k * nblk * 32 + 255) / 256, 256, 0, st>>>(cand_hist, img_hist, n_gt, nblk, k, rows_k_dev);
   pcl_rr_ngt_kernel<<<1, 64, 0, st>>>(n_gt, nblk, ngt_dev);
-  g_pcl_launches.fetch_add(5);
+  g_pcl_launches.fetch_add(6);
   e = cudaGetLastError();
   pcl_pool_free(buf, st);
   if (e != cudaSuccess) { pcl_set_error("re-rank launch failed: %s", cudaGetErrorString(e)); return PCL_ERR_CUDA; }

@@ -435,6 +435,7 @@ extern "C" int pcl_score(const pcl_cloud* c, const pcl_image* im, const float* p
   int rc = pcl_check_inputs(c, im, poses_p6_dev, p);
   if (rc) return rc;
   if (!loss_p_dev) { pcl_set_error("loss output is null"); return PCL_ERR_INVALID; }
+  PclUseGuard guard{c, im, (cudaStream_t)stream};
   return pcl_run_once(c, im, poses_p6_dev, p, false, loss_p_dev, count_p_dev, nullptr, (cudaStream_t)stream);
 }
 
@@ -443,6 +444,7 @@ extern "C" int pcl_loss_fwd_bwd(const pcl_cloud* c, const pcl_image* im, const f
   int rc = pcl_check_inputs(c, im, poses_b6_dev, b);
   if (rc) return rc;
   if (!loss_b_dev || !grad_b6_dev) { pcl_set_error("loss/grad output is null"); return PCL_ERR_INVALID; }
+  PclUseGuard guard{c, im, (cudaStream_t)stream};
   return pcl_run_once(c, im, poses_b6_dev, b, true, loss_b_dev, count_b_dev, grad_b6_dev, (cudaStream_t)stream);
 }
 

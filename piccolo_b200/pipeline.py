@@ -88,7 +88,8 @@ def localize_query(cloud: engine.Cloud, image: engine.Image, grid: torch.Tensor,
     mark("refine1")
     out = ref.read()
     best = out["loss"].argmin()
-    return {"pose": out["pose"][best], "loss": out["loss"][best], "index": best, "candidates": out["pose"], "losses": out["loss"],
+    b1 = best.reshape(1)                  # index_select, not out[...][best]: indexing with a 0-dim device tensor reads it back (host sync)
+    return {"pose": out["pose"].index_select(0, b1)[0], "loss": out["loss"].index_select(0, b1)[0], "index": best, "candidates": out["pose"], "losses": out["loss"],
             "start_index": idx}
 
 
@@ -104,6 +105,52 @@ def localize_query_host(xyz_h: torch.Tensor, rgb_h: torch.Tensor, img_h: torch.T
     out = localize_query(cloud, image, grid, cfg, img=img)
     res = torch.cat([out["pose"], out["loss"].reshape(1)]).cpu()
     return res[:6], float(res[6])
+
+
+def localize_stream(queries, cfg, device, num_split=(4, 4)):
+    """A stream of queries with HOST (pinned) buffers: `queries` yields (xyz_h, rgb_h, img_h, grid_h); yields
+    (pose (6,) cpu, loss float) per query, in order.  The upload and packing (Morton sort, clamp box, texel tables) of
+    query i+1 run on a side stream while query i is scored and refined on the current stream, so in steady state the
+    host->device copies cost nothing (they are ~10 % of a C2 query otherwise).  Every query is still uploaded in full."""
+    main = torch.cuda.current_stream(device)
+    side = torch.cuda.Stream(device)
+
+    def stage(q):
+        xyz_h, rgb_h, img_h, grid_h = q
+        with torch.cuda.stream(side):
+            xyz = xyz_h.to(device, non_blocking=True)
+            rgb = rgb_h.to(device, non_blocking=True)
+            cloud = engine.Cloud(xyz, rgb, cfg.out_of_room_quantile)
+            img = img_h.to(device, non_blocking=True)
+            grid = grid_h.to(device, non_blocking=True)
+            image = engine.Image(img)
+            ready = torch.cuda.Event()
+            ready.record(side)
+        return cloud, image, img, grid, ready
+
+    def launch(st):
+        cloud, image, img, grid, ready = st
+        main.wait_event(ready)
+        for t in (img, grid.trans, grid.rot) if isinstance(grid, StartGrid) else (img, grid):
+            t.record_stream(main)                         # allocated on the side stream, read on this one
+        out = localize_query(cloud, image, grid, cfg, img=img, num_split=num_split)
+        return torch.cat([out["pose"], out["loss"].reshape(1)])
+
+    it = iter(queries)
+    try:
+        cur = stage(next(it))
+    except StopIteration:
+        return
+    while cur is not None:
+        res_dev = launch(cur)                             # asynchronous: the GPU works on this query ...
+        try:
+            nxt = stage(next(it))                         # ... while the next one is uploaded and packed
+        except StopIteration:
+            nxt = None
+        res = res_dev.cpu()                               # the step's device->host read
+        del cur                                           # handles go back in stream order (the library waits for their last use)
+        yield res[:6], float(res[6])
+        cur = nxt
 
 
 def localize_query_sharded(cloud: engine.Cloud, image: engine.Image, grid: torch.Tensor, cfg, img: torch.Tensor = None, num_split=(4, 4),
