@@ -34,6 +34,8 @@ __global__ void pcl_grid_plan_kernel(const float* __restrict__ rot, const int R,
   __shared__ double s_R[PCL_GRID_MAX_ROT][9];
   __shared__ int s_group[PCL_GRID_MAX_ROT], s_base[PCL_GRID_MAX_ROT];
   const int j = threadIdx.x;
+  // the scoring kernel copies the whole plan into shared memory: no uninitialised tail
+  for (int i = j; i < (int)(sizeof(PclGridPlan) / 4); i += blockDim.x) reinterpret_cast<int*>(plan)[i] = 0;
   if (j < R) {
     const double y = rot[3 * j], p = rot[3 * j + 1], r = rot[3 * j + 2];
     const double cy = cos(y), sy = sin(y), cp = cos(p), sp = sin(p), cr = cos(r), sr = sin(r);

@@ -75,7 +75,9 @@ def _localize(cfg, writer, log_dir: str, dataset: str):
     main_ds = (getattr(cfg, "main_downsample_h", 1), getattr(cfg, "main_downsample_w", 1))
 
     past_pcd = ""
-    for trial, q in enumerate(datasets.synthetic_queries(cfg, dataset)):
+    query_source = datasets.queries(cfg, dataset)         # raises on dataset-selecting keys / dataset files it cannot honour
+    print(f"[piccolo_b200] {dataset}: SYNTHETIC rooms (the dataset file readers are outside this build's scope); records are named synthetic://...", flush=True)
+    for trial, q in enumerate(query_source):
         if past_pcd != q.pcd_name:
             xyz = torch.from_numpy(q.xyz_np).float().to(device)
             rgb = torch.from_numpy(q.rgb_np).float().to(device)
@@ -90,6 +92,8 @@ def _localize(cfg, writer, log_dir: str, dataset: str):
                 orig_img = (((orig_img / 255.) ** cfg.synth_gamma) * 255).astype(np.uint8)
             if getattr(cfg, "synth_wb", None):
                 for c, key in enumerate(("synth_r", "synth_g", "synth_b")):
+                    # clamped at 255: the reference casts first and clamps afterwards (localize.py:389-393), so its uint8 cast
+                    # WRAPS values above 255 and the clamp is a no-op; the clamp it evidently intends is what is done here
                     orig_img[..., c] = np.minimum(((orig_img[..., c] / 255.) * getattr(cfg, key)) * 255, 255).astype(np.uint8)
         raw_img = torch.from_numpy(orig_img).float().to(device) / 255.
         num_bins = getattr(cfg, "num_bins", 256)

@@ -144,3 +144,26 @@ def test_requantize_is_the_drivers_uint8_round_trip():
     x = torch.rand(64, 128, 3)
     want = torch.from_numpy((255 * x.numpy()).astype(np.uint8)).float() / 255.
     assert torch.equal(requantize(x), want)
+
+
+def test_dataset_provider_never_ignores_dataset_keys(tmp_path, monkeypatch):
+    """The drivers run on synthetic rooms only (the dataset file readers are out of scope): keys that select dataset
+    files, or dataset files on disk, must raise instead of being silently ignored; synthetic records say so by name."""
+    from types import SimpleNamespace
+    import pytest
+    from piccolo_b200 import datasets
+    ok = SimpleNamespace(area=None, room_name=None, gravity_aligned=True, visualize=False, split_name="extreme")
+    datasets.check_config(ok, "Stanford2D-3D-S")
+    for key, val in (("area", 3), ("room_name", "office_1"), ("scene_number", 2), ("split_name", "change_handheld"),
+                     ("gravity_aligned", False), ("visualize", True)):
+        bad = SimpleNamespace(**{key: val})
+        with pytest.raises(datasets.DatasetUnavailable):
+            datasets.check_config(bad, "OmniScenes")
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "data" / "stanford").mkdir(parents=True)
+    with pytest.raises(datasets.DatasetUnavailable):
+        datasets.check_config(ok, "Stanford2D-3D-S")
+    datasets.check_config(SimpleNamespace(synthetic=True), "Stanford2D-3D-S")
+    cfg = SimpleNamespace(synthetic=True, synthetic_points=2000, synthetic_queries=1, synthetic_height=32)
+    q = next(iter(datasets.queries(cfg, "Stanford2D-3D-S")))
+    assert q.filename.startswith("synthetic://") and q.pcd_name.startswith("synthetic://")
