@@ -53,7 +53,7 @@ def measured_hbm_peak():
 def ncu_traffic(key):
     """DRAM bytes per launch of the kernel from the committed ncu --set full capture (profiles/), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             return float(json.load(f)[key])
     except Exception:
         return None
@@ -389,20 +389,27 @@ def run_ours(args):
                                           "cooperative launch; figures are per iteration)",
                                 "bound": "hbm", "achieved": bwd_achieved, "peak": peak, "unit": "GB/s", "frac": bwd_achieved / peak,
                                 "traffic": ncu_traffic("C2_refine_launch_bytes") if default_size else None,
+                                "issue_frac": ncu_traffic("C2_refine_issue_frac") if default_size else None,
+                                "l1tex_frac": ncu_traffic("C2_refine_l1tex_frac") if default_size else None,
                                 "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_EVAL * cfg.num_input * args.n_points,
                                 "launch_us": bwd_launch_s * 1e6, "evals_per_s": cfg.num_input * args.n_points / bwd_launch_s,
                                 "iterations_per_launch": cfg.num_iter,
                                 "note": "one cooperative launch runs all iterations; achieved / algorithmic bytes / traffic / launch_us are per iteration "
-                                        "(launch duration / num_iter, CUDA events around the launch)"},
+                                        "(launch duration / num_iter, CUDA events around the launch).  The points of every CTA stay in shared memory "
+                                        "for the whole launch, so the point stream causes no DRAM/L2 traffic after the prologue (`traffic` is the cold "
+                                        "first touch of the texel table); the co-roofs are instruction issue (`issue_frac`, ncu: issue slots busy) and "
+                                        "the L1/TEX data stage (`l1tex_frac`), profiles/r2_ncu_full_refine_resident_C2.md"},
             "roofline_score": {"kernel": "pcl_grid_score_kernel<fmt> (structured-grid forward-only scoring, one launch for the 75x24 start grid; rotations related "
                                          "by an in-plane turn share transform/elevation/azimuth per point)", "bound": "hbm",
                                "achieved": sc_achieved, "peak": peak, "unit": "GB/s", "frac": sc_achieved / peak,
                                "traffic": ncu_traffic("C2_score_launch_bytes") if default_size else None,
+                               "issue_frac": ncu_traffic("C2_score_issue_frac") if default_size else None,
+                               "l1tex_frac": ncu_traffic("C2_score_l1tex_frac") if default_size else None,
                                "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_EVAL * P * args.n_points,
                                "launch_us": sc_launch_s * 1e6, "evals_per_s": P * args.n_points / sc_launch_s,
                                "note": "frac > 1 is possible: SURVEY 8d's figure charges one 24-byte point read per pose*point evaluation, while a loaded "
                                        "point is reused for all poses of a CTA (actual DRAM traffic: `traffic`); the kernel's real co-roofs are L1/TEX "
-                                       "gather wavefronts (83 %) and instruction issue (75 %), profiles/r1_ncu_full_grid_score_C2.md"},
+                                       "gather wavefronts (`l1tex_frac`) and instruction issue (`issue_frac`), profiles/r2_ncu_full_grid_score_C2.md"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 28, "sec_per_query": e2e_ms / e2e_steps * 1e-3,
                     "steps": e2e_steps, "mode": "stream of queries through pipeline.localize_stream (upload + packing of query i+1 overlap query i)",
                     "latency_sec_per_query": lat_ms * 1e-3},
@@ -415,7 +422,7 @@ def run_ours(args):
                                     "sample": f"24 of {P} grid poses forward-only ({r['score_s']:.1f} s) + 2 of {cfg.num_iter} refinement iterations B={cfg.num_input} "
                                               f"({r['refine_s']:.1f} s) of the same workload, oracle ATen-chain port, {torch.get_num_threads()} threads",
                                     "sec_per_query_extrapolated": q_evals / (r["evals"] / r["seconds"])}
-        # `roofline` = the kernel with the larger share of the step (ncu launch list: profiles/r1_launch_list_bench_C2.md); the two
+        # `roofline` = the kernel with the larger share of the step (ncu launch list: profiles/r2_launch_list_bench_C2.md); the two
         # phases are within a few per cent of each other at C2, so a near-tie goes to the refinement kernel (the lower fraction)
         line["roofline"] = dict(line["roofline_score"] if sum(score_ms) > 1.1 * sum(refine_ms) else line["roofline_refine"])
         if strong is not None:

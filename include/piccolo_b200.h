@@ -95,7 +95,9 @@ int pcl_cloud_bounds(const pcl_cloud* c, float* lo_hi);
 void pcl_cloud_destroy(pcl_cloud* c);
 
 /* ---- equirectangular panorama -------------------------------------------------------------- */
-/* img_hw3_dev: (H,W,3) float32 in [0,1].  Synchronises `stream` before returning. */
+/* img_hw3_dev: (H,W,3) float32 in [0,1]; must stay valid until the work enqueued on `stream` has run (a stream-ordered
+ * free is fine).  Formats other than F32 wait once on `stream` for a one-word answer (is the image exactly uint8/255
+ * data?), which selects the texel format; the table builds themselves are asynchronous. */
 int pcl_image_create(const float* img_hw3_dev, int h, int w, int format, void* stream, pcl_image** out);
 int pcl_image_format(const pcl_image* im);
 void pcl_image_destroy(pcl_image* im);

@@ -100,7 +100,13 @@ static int pcl_cloud_build(pcl_cloud* c, const float* xyz, const float* rgb, int
   const int threads = 256;
   const int blocks = (int)((n + threads - 1) / threads);
   unsigned int* perm = nullptr;
-  void* scratch = nullptr;
+  struct Scratch {                       // freed on every exit path, in stream order
+    void* p[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t st;
+    ~Scratch() { for (void* q : p) pcl_pool_free(q, st); }
+  } sc;
+  sc.st = st;
+  void*& scratch = sc.p[0];
   if (order == PCL_CLOUD_MORTON) {
     unsigned int* mm; unsigned int *k_in, *k_out; unsigned int *v_in, *v_out;
     size_t tmp_bytes = 0;
@@ -135,18 +141,17 @@ static int pcl_cloud_build(pcl_cloud* c, const float* xyz, const float* rgb, int
     if (i_hi > n - 1) i_hi = n - 1;
     size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (float*)nullptr, (float*)nullptr, (int)n, 0, 32, st);
-    void* tmp = nullptr; float* sorted = nullptr;
+    void*& tmp = sc.p[1];
     PCL_CUDA(pcl_pool_alloc(&tmp, tmp_bytes + 256, st));
-    PCL_CUDA(pcl_pool_alloc((void**)&sorted, sizeof(float) * (size_t)n, st));
+    PCL_CUDA(pcl_pool_alloc(&sc.p[2], sizeof(float) * (size_t)n, st));
+    float* sorted = (float*)sc.p[2];
     const float* axes[3] = {c->x, c->y, c->z};
     for (int k = 0; k < 3; ++k) {
       PCL_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, axes[k], sorted, (int)n, 0, 32, st));
       PCL_CUDA(cudaMemcpyAsync(c->lo_hi_dev + k, sorted + i_lo, sizeof(float), cudaMemcpyDeviceToDevice, st));
       PCL_CUDA(cudaMemcpyAsync(c->lo_hi_dev + 3 + k, sorted + i_hi, sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    pcl_pool_free(tmp, st); pcl_pool_free(sorted, st);
   }
-  pcl_pool_free(scratch, st);
   return PCL_OK;
 }
 
@@ -342,7 +347,8 @@ static int pcl_image_build(pcl_image* im, const float* img, int h, int w, int fo
     pcl_build_f32_kernel<<<grid, block, 0, st>>>(img, h, w, (float4*)im->data);
   }
   if (fmt != PCL_IMAGE_TEX) PCL_LAUNCH_CHECK();
-  PCL_CUDA(cudaStreamSynchronize(st));
+  // no synchronisation here: the table builds are ordered on `st` like every consumer of the handle (the only host wait
+  // of this function is the one-word "is it exact uint8/255 data" answer above, which picks the texel format)
   im->view.data = im->data;
   return PCL_OK;
 }

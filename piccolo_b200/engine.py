@@ -49,6 +49,7 @@ class Cloud:
                                             int(order), _stream(self.device), ctypes.byref(h)))
         self._h = h
         self.n = int(xyz_c.shape[0])
+        self.quantile = float(out_of_room_quantile)
         self._box = None
 
     def _bounds(self):
@@ -341,8 +342,17 @@ def _cached(key, tensors, build):
     return obj
 
 
-def get_cloud(xyz: torch.Tensor, rgb: torch.Tensor, q: float = 0.05) -> Cloud:
-    return _cached(_key(xyz, rgb, extra=("cloud", float(q))), (xyz, rgb), lambda: Cloud(xyz, rgb, q))
+def get_cloud(xyz: torch.Tensor, rgb: torch.Tensor, q: float = None) -> Cloud:
+    """The packed cloud of (xyz, rgb), built once per tensor pair.  `q` (out_of_room_quantile) only matters to the
+    refinement's clamp box: callers that do not care (scoring, re-rank) pass None and share whatever cloud is cached, so
+    a config with another quantile does not pack (Morton sort + three radix sorts) the same cloud twice per query."""
+    key = _key(xyz, rgb, extra=("cloud",))
+    hit = _CACHE.get(key)
+    if hit is not None and (q is None or abs(hit[0].quantile - float(q)) < 1e-12):
+        _CACHE.move_to_end(key)
+        return hit[0]
+    _CACHE.pop(key, None)
+    return _cached(key, (xyz, rgb), lambda: Cloud(xyz, rgb, 0.05 if q is None else q))
 
 
 def get_image(img: torch.Tensor, fmt="auto") -> Image:

@@ -15,8 +15,9 @@ def grid_poses(trans: torch.Tensor, rot: torch.Tensor) -> torch.Tensor:
     return torch.cat([trans.to(torch.float32).repeat_interleave(Rn, 0), rot.to(torch.float32).repeat(T, 1)], dim=1)
 
 
-def score_grid(img, xyz, rgb, trans, rot, q: float = 0.05) -> torch.Tensor:
-    """loss_table (T,R) of utils.py:481-499 from one kernel launch (structured-grid scoring, pcl_grid.cu)."""
+def score_grid(img, xyz, rgb, trans, rot, q: float = None) -> torch.Tensor:
+    """loss_table (T,R) of utils.py:481-499 from one kernel launch (structured-grid scoring, pcl_grid.cu).
+    The clamp-box quantile plays no part in scoring: q=None shares whatever packed cloud is cached."""
     cloud = engine.get_cloud(xyz, rgb, q)
     image = engine.get_image(img)
     loss, _ = engine.score_grid(cloud, image, trans, rot)
@@ -77,7 +78,7 @@ def trim_input_hist_secondary(img: torch.Tensor, xyz: torch.Tensor, rgb: torch.T
                               num_input: int, num_split_h: int, num_split_w: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """Same contract as the reference (utils.py:510-588): the `num_input` candidates whose rendered colour
     histograms intersect the query's best, in descending order of intersection."""
-    cloud = engine.get_cloud(xyz, rgb, 0.05)
+    cloud = engine.get_cloud(xyz, rgb)           # the clamp-box quantile plays no part in the re-rank
     poses = torch.cat([trans.reshape(-1, 3), rot.reshape(-1, 3)], dim=1).to(torch.float32)
     scores = engine.hist_rerank(cloud, img, poses, num_split_h, num_split_w)
     order = engine.topk(-scores, min(num_input, scores.numel()))

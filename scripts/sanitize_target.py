@@ -9,9 +9,10 @@ sc = synth.make_scene(7001, 64, 128, seed=2)
 xyz, rgb, img = [torch.from_numpy(a).to(dev) for a in (sc.xyz, sc.rgb, sc.img)]
 rng = np.random.default_rng(0)
 poses = torch.from_numpy(np.stack([sc.gt_pose + np.concatenate([rng.normal(0, 0.3, 3), rng.normal(0, 0.2, 3)]) for _ in range(70)]).astype(np.float32)).to(dev)
-for order in (0, 1):
+LIGHT = os.environ.get("PCL_SANITIZE_LIGHT") == "1"     # initcheck is ~50x slower than the other tools: one order, two formats
+for order in ((1,) if LIGHT else (0, 1)):
     cloud = engine.Cloud(xyz, rgb, 0.05, order)
-    for fmt in ("auto", "f16d", "u8q", "u8p", "tex", "f32"):
+    for fmt in (("auto", "u8q") if LIGHT else ("auto", "f16d", "u8q", "u8p", "tex", "f32")):
         image = engine.Image(img, fmt)
         loss, cnt = engine.score(cloud, image, poses)
         from piccolo_b200.utils import generate_rot_points
