@@ -206,17 +206,25 @@ def test_c1_full_query_matches_reference_run(golden):
     np.testing.assert_allclose(sc.gt_pose, g["gt_pose"])
     xyz, rgb, img = cu(sc.xyz), cu(sc.rgb), cu(sc.img)
     in_t, in_r = make_input(img, xyz, rgb, cfg.num_input, get_init_dict(cfg), cfg.criterion, cfg.num_intermediate)
-    ours = {tuple(np.round(np.concatenate([a, b]), 4)) for a, b in zip(in_t.cpu().numpy(), in_r.cpu().numpy())}
-    theirs = {tuple(np.round(np.concatenate([a, b]), 4)) for a, b in zip(g["input_trans"], g["input_rot"])}
-    # the reference's re-rank renders with a racy index_put_: demand a large overlap of the 6 selected starts and
-    # the same winner of the re-rank
-    assert len(ours & theirs) >= 4, (ours, theirs)
-    np.testing.assert_allclose(in_t[0].cpu().numpy(), g["input_trans"][0], atol=1e-5)
-    np.testing.assert_allclose(in_r[0].cpu().numpy(), g["input_rot"][0], atol=1e-5)
+    # Start selection: the reference returns the SAME six starts in the same order when run with 8 threads (query_c1.npz)
+    # and with 4 threads (variants.npz: c1_*_t4, tests/golden/make_golden.py variants) — its selection is stable on this
+    # query, so ours must be identical, row by row (no hand-picked 4-of-6 slack).
+    v = golden("variants")
+    np.testing.assert_allclose(v["c1_input_trans_t4"], g["input_trans"], atol=1e-6)
+    np.testing.assert_allclose(v["c1_input_rot_t4"], g["input_rot"], atol=1e-6)
+    np.testing.assert_allclose(in_t.cpu().numpy(), g["input_trans"], atol=1e-5)
+    np.testing.assert_allclose(in_r.cpu().numpy(), g["input_rot"], atol=1e-5)
     res = omniloc_all(img, xyz, rgb, in_t, in_r, cfg)
     best = int(np.argmin([float(r[2]) for r in res]))
+    assert best == int(g["best"]) == int(v["c1_best_t4"])
     t, R = res[best][0].numpy().reshape(3), res[best][1].numpy().astype(np.float64)
     tr, Rr = g["final_t"][int(g["best"])], g["final_R"][int(g["best"])].astype(np.float64)
-    ang = np.rad2deg(np.arccos(np.clip((np.trace(R.T @ Rr) - 1) / 2, -1, 1)))
-    assert np.linalg.norm(t - tr) < 0.01 and ang < 0.25, (t, tr, ang)          # 1 cm; rotation within the end-state jitter
+    t4, R4 = v["c1_final_t_t4"][best], v["c1_final_R_t4"][best].astype(np.float64)
+    rot = lambda A, B: np.rad2deg(np.arccos(np.clip((np.trace(A.T @ B) - 1) / 2, -1, 1)))
+    # End state: 1 cm / 0.1 deg (north star), widened only to 1.5 x the distance between the reference's OWN two runs
+    # (Adam amplifies rounding noise; its 8- and 4-thread runs end 2.5 mm apart on the winner and up to 1.1 cm apart on the
+    # other candidates).  Ours must be that close to at least one of the two reference runs.
+    gate_t = max(0.01, 1.5 * np.linalg.norm(tr - t4)); gate_r = max(0.1, 1.5 * rot(Rr, R4))
+    d = min((np.linalg.norm(t - a_), rot(R, B_)) for a_, B_ in ((tr, Rr), (t4, R4)))
+    assert d[0] < gate_t and d[1] < gate_r, (t, tr, t4, d, gate_t, gate_r)
     assert np.linalg.norm(t - sc.gt_pose[:3]) < 0.05
