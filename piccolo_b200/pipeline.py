@@ -107,13 +107,25 @@ def localize_query_host(xyz_h: torch.Tensor, rgb_h: torch.Tensor, img_h: torch.T
     return res[:6], float(res[6])
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    """ONE upload stream per device for the life of the process: the caching allocators (torch's and the library's
+    stream-ordered pool) keep their free lists per stream, so a fresh stream per call would re-allocate every buffer."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return _SIDE_STREAMS[key]
+
+
 def localize_stream(queries, cfg, device, num_split=(4, 4)):
     """A stream of queries with HOST (pinned) buffers: `queries` yields (xyz_h, rgb_h, img_h, grid_h); yields
     (pose (6,) cpu, loss float) per query, in order.  The upload and packing (Morton sort, clamp box, texel tables) of
     query i+1 run on a side stream while query i is scored and refined on the current stream, so in steady state the
     host->device copies cost nothing (they are ~10 % of a C2 query otherwise).  Every query is still uploaded in full."""
     main = torch.cuda.current_stream(device)
-    side = torch.cuda.Stream(device)
+    side = _side_stream(device)
 
     def stage(q):
         xyz_h, rgb_h, img_h, grid_h = q
