@@ -110,12 +110,46 @@ __device__ __forceinline__ void pcl_rf_zero(PclAcc& a) {
   a.se = -0.f; a.sm = -0.f; a.ax = -0.f; a.ay = -0.f; a.az = -0.f; a.tx = -0.f; a.ty = -0.f; a.tz = -0.f;   // -0 + x == x
 }
 
-// fp32 register sums of one pose -> the warp's private fp64 shared-memory row
-__device__ __forceinline__ void pcl_rf_flush(PclAcc& a, double* __restrict__ row8, const int lane) {
-  float v[8] = {a.se, a.sm, a.ax, a.ay, a.az, a.tx, a.ty, a.tz};
-  pcl_rf_warp_reduce8(v, lane);
-  if ((lane & 3) == 0) row8[pcl_rf_bfly_index(lane)] += (double)v[0];
-  pcl_rf_zero(a);
+// fp32 register sums of ALL poses of the block -> the warp's private fp64 shared-memory rows.  The NPB butterflies are
+// issued stage by stage side by side (the shuffles of a stage are independent across poses): the dependent chain of
+// one reduction instead of NPB of them in a row.  Poses beyond np hold -0 sums and add nothing.
+template <int NPB>
+__device__ __forceinline__ void pcl_rf_flush_all(PclAcc (&acc)[NPB], double (*rows)[PCL_NSUM], const int lane) {
+  float v[NPB][8];
+#pragma unroll
+  for (int p = 0; p < NPB; ++p) {
+    v[p][0] = acc[p].se; v[p][1] = acc[p].sm; v[p][2] = acc[p].ax; v[p][3] = acc[p].ay;
+    v[p][4] = acc[p].az; v[p][5] = acc[p].tx; v[p][6] = acc[p].ty; v[p][7] = acc[p].tz;
+  }
+  int n = 8;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    if (n > 1) {
+      const bool up = (lane & o) != 0;
+      n >>= 1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < n) {
+#pragma unroll
+          for (int p = 0; p < NPB; ++p) {
+            const float send = up ? v[p][i] : v[p][i + n];
+            const float keep = up ? v[p][i + n] : v[p][i];
+            v[p][i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int p = 0; p < NPB; ++p) v[p][0] += __shfl_xor_sync(0xffffffffu, v[p][0], o);
+    }
+  }
+  if ((lane & 3) == 0) {
+    const int k = pcl_rf_bfly_index(lane);
+#pragma unroll
+    for (int p = 0; p < NPB; ++p) rows[p][k] += (double)v[p][0];
+  }
+#pragma unroll
+  for (int p = 0; p < NPB; ++p) pcl_rf_zero(acc[p]);
 }
 
 // Streamed (non-resident) point loads: read-only path, no L1 allocation, and marked evict-first in L2 — a cloud that is
@@ -146,7 +180,14 @@ template <int FMT, int NPB, typename Hook>
 __device__ __forceinline__ void pcl_rf_phase(const PclCloudView& C, const PclImage& I, const PclPose* __restrict__ s_pose, const int np,
                                              const long long c_begin, const long long c_end, const float* __restrict__ s_pts, const int res_n,
                                              const int res_stride, double (*s_acc)[NPB][PCL_NSUM],
-                                             const int tid, const int lane, const int warp, const Hook& hook) {
+                                             const int tid, const int lane, const int warp, const Hook& hook
+#ifdef PCL_RF_TRACE
+                                             , long long* trace
+#endif
+                                             ) {
+#ifdef PCL_RF_TRACE
+  const long long tr0 = clock64();
+#endif
   // each warp owns its rows of s_acc: no CTA-wide synchronisation until the end of the phase
   for (int i = lane; i < NPB * PCL_NSUM; i += 32) (&s_acc[warp][0][0])[i] = 0.0;
   __syncwarp();
@@ -187,12 +228,13 @@ __device__ __forceinline__ void pcl_rf_phase(const PclCloudView& C, const PclIma
     }
     if (++pending == PCL_RF_FLUSH) {
       pending = 0;
-#pragma unroll
-      for (int p = 0; p < NPB; ++p)
-        if (p < np) pcl_rf_flush(acc[p], s_acc[warp][p], lane);
+      pcl_rf_flush_all<NPB>(acc, s_acc[warp], lane);
     }
   }
 
+#ifdef PCL_RF_TRACE
+  const long long tr1 = clock64();
+#endif
   hook();
 
   // remainder (< 1024 points): thread t takes pose t % np and every S-th point from slot t / np, S = 256 / np
@@ -238,10 +280,14 @@ __device__ __forceinline__ void pcl_rf_phase(const PclCloudView& C, const PclIma
       acc[p].tx += mine ? ar.tx : 0.f; acc[p].ty += mine ? ar.ty : 0.f; acc[p].tz += mine ? ar.tz : 0.f;
     }
   }
-#pragma unroll
-  for (int p = 0; p < NPB; ++p)
-    if (p < np) pcl_rf_flush(acc[p], s_acc[warp][p], lane);
+  pcl_rf_flush_all<NPB>(acc, s_acc[warp], lane);
+#ifdef PCL_RF_TRACE
+  const long long tr2 = clock64();
+#endif
   __syncthreads();
+#ifdef PCL_RF_TRACE
+  if (trace) { trace[0] += tr1 - tr0; trace[1] += tr2 - tr1; trace[2] += clock64() - tr2; }
+#endif
 }
 
 // the CTA's record of a phase: rec8[p*8 + s] = Σ_warps s_acc[w][p][s]   (threads < np*8)
@@ -425,6 +471,12 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
 
   int ph = 0;
   long long t_busy = 0, t_wait = 0, n_hit = 0;
+#ifdef PCL_RF_TRACE
+  long long trace[3] = {0, 0, 0};
+  __shared__ unsigned long long s_trace[4];
+  if (tid < 4) s_trace[tid] = 0ull;
+  __syncthreads();
+#endif
   for (int it = 0; it < ps.num_iter; ++it) {
     for (int b = 0; b < ps.nblk; ++b, ++ph) {
       const int buf = ph & 1;
@@ -454,7 +506,11 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
         if (lane == 0) s_pref[buf ^ 1] = ph + 1;
       };
       const long long c1 = ps.dbg ? clock64() : 0;
-      pcl_rf_phase<FMT, NPB>(ps.C, ps.I, s_pose[buf], np, c_begin, c_end, s_pts, res_n, res_stride, s_acc[buf], tid, lane, warp, hook);
+      pcl_rf_phase<FMT, NPB>(ps.C, ps.I, s_pose[buf], np, c_begin, c_end, s_pts, res_n, res_stride, s_acc[buf], tid, lane, warp, hook
+#ifdef PCL_RF_TRACE
+                             , trace
+#endif
+                             );
       if (ps.dbg) { t_wait += c1 - c0; t_busy += clock64() - c1; }
       if (warp == 0) {
         if (lane < np * PCL_NSUM) {
@@ -473,6 +529,20 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
       }
     }
   }
+#ifdef PCL_RF_TRACE
+  if (ps.dbg) {      // per CTA: mean over warps of {cycles in full groups, remainder + flush, waiting at the phase barrier}, and the largest barrier wait
+    if (lane == 0) {
+      atomicAdd(&s_trace[0], (unsigned long long)trace[0]); atomicAdd(&s_trace[1], (unsigned long long)trace[1]);
+      atomicAdd(&s_trace[2], (unsigned long long)trace[2]); atomicMax(&s_trace[3], (unsigned long long)trace[2]);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      ps.dbg[4 * (size_t)cta] = s_trace[0] / PCL_RF_WARPS; ps.dbg[4 * (size_t)cta + 1] = s_trace[1] / PCL_RF_WARPS;
+      ps.dbg[4 * (size_t)cta + 2] = s_trace[2] / PCL_RF_WARPS; ps.dbg[4 * (size_t)cta + 3] = s_trace[3];
+    }
+    return;
+  }
+#endif
   if (ps.dbg && tid == 0) {
     ps.dbg[4 * (size_t)cta] = (unsigned long long)t_busy; ps.dbg[4 * (size_t)cta + 1] = (unsigned long long)t_wait;
     ps.dbg[4 * (size_t)cta + 2] = (unsigned long long)n_hit; ps.dbg[4 * (size_t)cta + 3] = 0;
@@ -503,7 +573,11 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
   const long long n_pts = ps.p_end - ps.p_begin;
   const long long c_begin = ps.p_begin + n_pts * (long long)cta / G;
   const long long c_end = ps.p_begin + n_pts * (long long)(cta + 1) / G;
-  pcl_rf_phase<FMT, NPB>(ps.C, ps.I, s_pose, np, c_begin, c_end, nullptr, 0, 0, s_acc, tid, lane, warp, PclRfNoHook());
+  pcl_rf_phase<FMT, NPB>(ps.C, ps.I, s_pose, np, c_begin, c_end, nullptr, 0, 0, s_acc, tid, lane, warp, PclRfNoHook()
+#ifdef PCL_RF_TRACE
+                         , nullptr
+#endif
+                         );
   double* rec = ps.rec[0] + (size_t)b * G * PCL_RF_MAXNPB * PCL_NSUM;
   if (tid < np * PCL_NSUM) rec[(size_t)cta * PCL_RF_MAXNPB * PCL_NSUM + tid] = pcl_rf_cta_sum<NPB>(s_acc, tid);
   __threadfence();
