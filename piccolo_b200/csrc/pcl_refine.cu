@@ -156,7 +156,7 @@ static int pcl_refine_run_fused(pcl_refine* r, const pcl_cloud* c, const pcl_ima
     // keep >= 60 KB of the 256 KB array as L1 for the texel gather: 28 KB (the next carve-out step) was measured slower
     // than not keeping the points at all
     const long long budget = (long long)(optin < 196 * 1024 ? optin : 196 * 1024) - PCL_RF_SMEM_STATIC;
-    const long long cap = budget / 24 / 32 * 32;
+    const long long cap = budget / (PCL_RF_ROWF * (long long)sizeof(float)) * PCL_RF_THREADS;   // whole rows of 512 points
     const long long per_cta = (n_pts + G - 1) / G;
     long long res = per_cta <= cap ? per_cta : (per_cta <= 3 * cap ? cap / PCL_RF_GROUP * PCL_RF_GROUP : 0);
     if (pcl_opt(PCL_OPT_RF_RES) == 0 || cap <= 0) res = 0;

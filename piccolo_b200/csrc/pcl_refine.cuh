@@ -35,9 +35,13 @@
 #define PCL_RF_WARPS (PCL_RF_THREADS / 32)
 #define PCL_RF_CTAS_PER_SM (512 / PCL_RF_THREADS)
 #define PCL_RF_GROUP (PCL_RF_KK * PCL_RF_THREADS)
+#define PCL_RF_ROWF (6 * PCL_RF_THREADS)   // floats of a resident row of PCL_RF_THREADS points in shared memory
 #define PCL_RF_FLUSH 8          // groups between two flushes of the fp32 register sums into the fp64 shared-memory row
 #define PCL_RF_MAXRANKS 8
 #define PCL_RF_SMEM_STATIC (20 * 1024)   // upper bound of the persistent kernel's static shared memory (checked by static_assert)
+
+// dynamic shared memory of `res_pts` resident points (whole rows)
+inline size_t pcl_rf_res_bytes(int res_pts) { return (size_t)((res_pts + PCL_RF_THREADS - 1) / PCL_RF_THREADS) * PCL_RF_ROWF * sizeof(float); }
 
 struct PclRfParams {
   PclCloudView C;
@@ -173,13 +177,14 @@ struct PclRfNoHook { __device__ __forceinline__ void operator()() const {} };
 // `hook` runs once, after the full groups and before the remainder (the persistent kernel prefetches the next phase's
 // poses there with one warp).
 //
-// Resident points: s_pts (nullable) holds the first `res_n` points of the range as SoA arrays x|y|z|r|g|b of `res_stride`
-// floats each (the persistent kernel copies them once per launch): groups that lie inside read shared memory instead of
-// global memory, the remainder does when the whole range is resident.
+// Resident points: s_pts (nullable) holds the first `res_n` points of the range in rows of 512 points, each row as
+// x[512] | y[512] | z[512] | r[512] | g[512] | b[512] (the persistent kernel copies them once per launch): a thread's 24
+// values of a group sit at compile-time offsets from ONE base address.  Groups that lie inside read shared memory
+// instead of global memory, the remainder does when the whole range is resident.
 template <int FMT, int NPB, typename Hook>
 __device__ __forceinline__ void pcl_rf_phase(const PclCloudView& C, const PclImage& I, const PclPose* __restrict__ s_pose, const int np,
                                              const long long c_begin, const long long c_end, const float* __restrict__ s_pts, const int res_n,
-                                             const int res_stride, double (*s_acc)[NPB][PCL_NSUM],
+                                             double (*s_acc)[NPB][PCL_NSUM],
                                              const int tid, const int lane, const int warp, const Hook& hook
 #ifdef PCL_RF_TRACE
                                              , long long* trace
@@ -203,12 +208,12 @@ __device__ __forceinline__ void pcl_rf_phase(const PclCloudView& C, const PclIma
   for (long long g = 0; g < n_groups; ++g, i0 += PCL_RF_GROUP) {
     float px[PCL_RF_KK], py[PCL_RF_KK], pz[PCL_RF_KK], cr[PCL_RF_KK], cg[PCL_RF_KK], cb[PCL_RF_KK];
     if ((int)(g + 1) * PCL_RF_GROUP <= res_n) {                  // CTA-uniform: the group is resident
-      const float* s = s_pts + (int)g * PCL_RF_GROUP + tid;
+      const float* s = s_pts + (int)g * (PCL_RF_KK * PCL_RF_ROWF) + tid;
 #pragma unroll
       for (int j = 0; j < PCL_RF_KK; ++j) {
-        const float* sj = s + j * PCL_RF_THREADS;
-        px[j] = sj[0]; py[j] = sj[res_stride]; pz[j] = sj[2 * res_stride];
-        cr[j] = sj[3 * res_stride]; cg[j] = sj[4 * res_stride]; cb[j] = sj[5 * res_stride];
+        const float* sj = s + j * PCL_RF_ROWF;
+        px[j] = sj[0]; py[j] = sj[PCL_RF_THREADS]; pz[j] = sj[2 * PCL_RF_THREADS];
+        cr[j] = sj[3 * PCL_RF_THREADS]; cg[j] = sj[4 * PCL_RF_THREADS]; cb[j] = sj[5 * PCL_RF_THREADS];
       }
     } else {
 #pragma unroll
@@ -241,6 +246,7 @@ __device__ __forceinline__ void pcl_rf_phase(const PclCloudView& C, const PclIma
   const long long rem0 = c_begin + n_groups * PCL_RF_GROUP;
   const int r = (int)(c_end - rem0);
   const bool rem_res = (long long)res_n >= c_end - c_begin;      // the whole range is resident
+  const int rem_off = (int)(rem0 - c_begin);
   if (r > 0) {
     // tid / np and THREADS / np for np <= 4 by multiply-shift (exact for tid <= 65535 / 4)
     const unsigned int inv = np == 1 ? 65536u : np == 2 ? 32768u : np == 3 ? 21846u : 16384u;
@@ -259,9 +265,10 @@ __device__ __forceinline__ void pcl_rf_phase(const PclCloudView& C, const PclIma
           ok[j] = m < r;
           const int mm = ok[j] ? m : slot;                    // masked slots re-read a valid point and are discarded
           if (rem_res) {
-            const float* sj = s_pts + (int)(rem0 - c_begin) + mm;
-            px[j] = sj[0]; py[j] = sj[res_stride]; pz[j] = sj[2 * res_stride];
-            cr[j] = sj[3 * res_stride]; cg[j] = sj[4 * res_stride]; cb[j] = sj[5 * res_stride];
+            const int idx = rem_off + mm;                     // (the remainder starts on a row boundary: whole groups precede it)
+            const float* sj = s_pts + (idx / PCL_RF_THREADS) * PCL_RF_ROWF + (idx % PCL_RF_THREADS);
+            px[j] = sj[0]; py[j] = sj[PCL_RF_THREADS]; pz[j] = sj[2 * PCL_RF_THREADS];
+            cr[j] = sj[3 * PCL_RF_THREADS]; cg[j] = sj[4 * PCL_RF_THREADS]; cb[j] = sj[5 * PCL_RF_THREADS];
           } else {
             const long long i = rem0 + mm;
             px[j] = __ldg(C.x + i); py[j] = __ldg(C.y + i); pz[j] = __ldg(C.z + i);
@@ -274,10 +281,11 @@ __device__ __forceinline__ void pcl_rf_phase(const PclCloudView& C, const PclIma
     }
 #pragma unroll
     for (int p = 0; p < NPB; ++p) {
-      const bool mine = (p == p_t);
-      acc[p].se += mine ? ar.se : 0.f; acc[p].sm += mine ? ar.sm : 0.f;
-      acc[p].ax += mine ? ar.ax : 0.f; acc[p].ay += mine ? ar.ay : 0.f; acc[p].az += mine ? ar.az : 0.f;
-      acc[p].tx += mine ? ar.tx : 0.f; acc[p].ty += mine ? ar.ty : 0.f; acc[p].tz += mine ? ar.tz : 0.f;
+      if (p == p_t) {                                            // predicated adds
+        acc[p].se += ar.se; acc[p].sm += ar.sm;
+        acc[p].ax += ar.ax; acc[p].ay += ar.ay; acc[p].az += ar.az;
+        acc[p].tx += ar.tx; acc[p].ty += ar.ty; acc[p].tz += ar.tz;
+      }
     }
   }
   pcl_rf_flush_all<NPB>(acc, s_acc[warp], lane);
@@ -404,7 +412,7 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
   __shared__ PclRefineState s_state[PCL_RF_MAXB];                // service CTA only
   __shared__ float s_evalp[PCL_RF_MAXB][6];
   __shared__ int s_pref[2];                                      // phase whose poses sit in s_pose[parity]
-  extern __shared__ __align__(16) float s_pts[];                 // resident points: x|y|z|r|g|b, res_stride floats each
+  extern __shared__ __align__(16) float s_pts[];                 // resident points in rows of 512: x|y|z|r|g|b, 512 floats each
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x, G = ps.G, n_rec = G * ps.nranks;
@@ -460,12 +468,12 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
   if (tid < 2) s_pref[tid] = -1;
   // resident points: copied once, read by every phase of every iteration (no HBM/L2 traffic and no long-latency load for
   // the point stream after this prologue; the only global loads of an iteration are the texel gathers)
-  const int res_stride = (ps.res_pts + 31) & ~31;
   const int res_n = (int)min((long long)ps.res_pts, c_end - c_begin);
   for (int k = tid; k < res_n; k += PCL_RF_THREADS) {
     const long long i = c_begin + k;
-    s_pts[k] = __ldg(ps.C.x + i); s_pts[res_stride + k] = __ldg(ps.C.y + i); s_pts[2 * res_stride + k] = __ldg(ps.C.z + i);
-    s_pts[3 * res_stride + k] = __ldg(ps.C.r + i); s_pts[4 * res_stride + k] = __ldg(ps.C.g + i); s_pts[5 * res_stride + k] = __ldg(ps.C.b + i);
+    float* d = s_pts + (k / PCL_RF_THREADS) * PCL_RF_ROWF + (k % PCL_RF_THREADS);
+    d[0] = __ldg(ps.C.x + i); d[PCL_RF_THREADS] = __ldg(ps.C.y + i); d[2 * PCL_RF_THREADS] = __ldg(ps.C.z + i);
+    d[3 * PCL_RF_THREADS] = __ldg(ps.C.r + i); d[4 * PCL_RF_THREADS] = __ldg(ps.C.g + i); d[5 * PCL_RF_THREADS] = __ldg(ps.C.b + i);
   }
   __syncthreads();
 
@@ -506,7 +514,7 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
         if (lane == 0) s_pref[buf ^ 1] = ph + 1;
       };
       const long long c1 = ps.dbg ? clock64() : 0;
-      pcl_rf_phase<FMT, NPB>(ps.C, ps.I, s_pose[buf], np, c_begin, c_end, s_pts, res_n, res_stride, s_acc[buf], tid, lane, warp, hook
+      pcl_rf_phase<FMT, NPB>(ps.C, ps.I, s_pose[buf], np, c_begin, c_end, s_pts, res_n, s_acc[buf], tid, lane, warp, hook
 #ifdef PCL_RF_TRACE
                              , trace
 #endif
@@ -573,7 +581,7 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
   const long long n_pts = ps.p_end - ps.p_begin;
   const long long c_begin = ps.p_begin + n_pts * (long long)cta / G;
   const long long c_end = ps.p_begin + n_pts * (long long)(cta + 1) / G;
-  pcl_rf_phase<FMT, NPB>(ps.C, ps.I, s_pose, np, c_begin, c_end, nullptr, 0, 0, s_acc, tid, lane, warp, PclRfNoHook()
+  pcl_rf_phase<FMT, NPB>(ps.C, ps.I, s_pose, np, c_begin, c_end, nullptr, 0, s_acc, tid, lane, warp, PclRfNoHook()
 #ifdef PCL_RF_TRACE
                          , nullptr
 #endif
@@ -604,7 +612,7 @@ template <int FMT> cudaError_t pcl_rf_launch_iter(const PclRfParams& ps, unsigne
                    : ps.npb == 2 ? (const void*)pcl_refine_persistent_kernel<FMT, 2>                                                \
                    : ps.npb == 3 ? (const void*)pcl_refine_persistent_kernel<FMT, 3>                                                \
                                  : (const void*)pcl_refine_persistent_kernel<FMT, 4>;                                               \
-    const size_t smem = (size_t)6 * ((ps.res_pts + 31) & ~31) * sizeof(float);                                                      \
+    const size_t smem = pcl_rf_res_bytes(ps.res_pts);                                                      \
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                               \
     if (e != cudaSuccess) return e;                                                                                                 \
     return cudaLaunchCooperativeKernel(fn, dim3(ps.G + 1), dim3(PCL_RF_THREADS), args, smem, st);                                   \
