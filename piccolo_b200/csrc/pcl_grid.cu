@@ -45,34 +45,38 @@ __global__ void pcl_grid_plan_kernel(const float* __restrict__ rot, const int R,
     s_R[j][6] = -sp;     s_R[j][7] = cp * sr;                s_R[j][8] = cp * cr;
   }
   __syncthreads();
-  if (j != 0) return;
-  int NG = 0;
-  for (int a = 0; a < R; ++a) {
-    int g = -1;
-    for (int k = 0; k < NG && g < 0; ++k) {
-      const int b = s_base[k];
-      const double d0 = s_R[a][6] - s_R[b][6], d1 = s_R[a][7] - s_R[b][7], d2 = s_R[a][8] - s_R[b][8];
-      if (fabs(d0) < PCL_GRID_TOL && fabs(d1) < PCL_GRID_TOL && fabs(d2) < PCL_GRID_TOL) g = k;
-    }
-    if (g < 0) { g = NG; s_base[NG++] = a; }
-    s_group[a] = g;
-  }
-  plan->R = R; plan->NG = NG;
-  int slot = 0;
-  for (int g = 0; g < NG; ++g) {
-    const int b = s_base[g];
-    plan->g_start[g] = slot;
-    plan->base_ypr[g][0] = rot[3 * b]; plan->base_ypr[g][1] = rot[3 * b + 1]; plan->base_ypr[g][2] = rot[3 * b + 2];
+  __shared__ int s_slot[PCL_GRID_MAX_ROT];
+  if (j == 0) {                                                  // the greedy grouping is sequential (integer work only)
+    int NG = 0;
     for (int a = 0; a < R; ++a) {
-      if (s_group[a] != g) continue;
-      // M = R_a R_bᵀ = Rz(delta): M00 = row0(a)·row0(b), M10 = row1(a)·row0(b)
-      const double m00 = s_R[a][0] * s_R[b][0] + s_R[a][1] * s_R[b][1] + s_R[a][2] * s_R[b][2];
-      const double m10 = s_R[a][3] * s_R[b][0] + s_R[a][4] * s_R[b][1] + s_R[a][5] * s_R[b][2];
-      plan->slot_rot[slot] = a;
-      plan->slot_delta[slot] = (a == b) ? 0.0f : (float)atan2(m10, m00);
-      ++slot;
+      int g = -1;
+      for (int k = 0; k < NG && g < 0; ++k) {
+        const int b = s_base[k];
+        const double d0 = s_R[a][6] - s_R[b][6], d1 = s_R[a][7] - s_R[b][7], d2 = s_R[a][8] - s_R[b][8];
+        if (fabs(d0) < PCL_GRID_TOL && fabs(d1) < PCL_GRID_TOL && fabs(d2) < PCL_GRID_TOL) g = k;
+      }
+      if (g < 0) { g = NG; s_base[NG++] = a; }
+      s_group[a] = g;
     }
-    plan->g_count[g] = slot - plan->g_start[g];
+    plan->R = R; plan->NG = NG;
+    int slot = 0;
+    for (int g = 0; g < NG; ++g) {
+      const int b = s_base[g];
+      plan->g_start[g] = slot;
+      plan->base_ypr[g][0] = rot[3 * b]; plan->base_ypr[g][1] = rot[3 * b + 1]; plan->base_ypr[g][2] = rot[3 * b + 2];
+      for (int a = 0; a < R; ++a)
+        if (s_group[a] == g) s_slot[a] = slot++;
+      plan->g_count[g] = slot - plan->g_start[g];
+    }
+  }
+  __syncthreads();
+  if (j < R) {                                                   // one thread per rotation: its azimuth offset against the group's base
+    const int a = j, b = s_base[s_group[a]];
+    // M = R_a R_bᵀ = Rz(delta): M00 = row0(a)·row0(b), M10 = row1(a)·row0(b)
+    const double m00 = s_R[a][0] * s_R[b][0] + s_R[a][1] * s_R[b][1] + s_R[a][2] * s_R[b][2];
+    const double m10 = s_R[a][3] * s_R[b][0] + s_R[a][4] * s_R[b][1] + s_R[a][5] * s_R[b][2];
+    plan->slot_rot[s_slot[a]] = a;
+    plan->slot_delta[s_slot[a]] = (a == b) ? 0.0f : (float)atan2(m10, m00);
   }
 }
 

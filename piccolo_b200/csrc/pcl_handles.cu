@@ -379,10 +379,49 @@ __global__ void pcl_topk_keys_kernel(const float* __restrict__ loss, long long n
   idx[i] = i;
 }
 
+// Small inputs (the start grids of the shipped protocols: 1 320 - 4 096 poses; the 50 re-ranked candidates): ONE CTA sorts
+// 64-bit keys [order-preserving float bits | index] in shared memory with a bitonic network — the index in the low bits
+// IS the "ties -> lower index" rule, the canonical NaN maps above +inf.  One launch instead of the ~10 of the radix sort.
+#define PCL_TOPK_SMALL 4096
+__global__ void __launch_bounds__(1024) pcl_topk_small_kernel(const float* __restrict__ loss, const int n, const int npow2, const int k,
+                                                              long long* __restrict__ idx_k) {
+  extern __shared__ unsigned long long s_key[];
+  for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (i < n) {
+      const float v = loss[i];
+      unsigned int u = isnan(v) ? 0x7fc00000u : (v == 0.0f ? 0u : __float_as_uint(v));
+      u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;                // ascending unsigned order == ascending float order
+      key = ((unsigned long long)u << 32) | (unsigned int)i;
+    }
+    s_key[i] = key;
+  }
+  __syncthreads();
+  for (int size = 2; size <= npow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (npow2 >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long a = s_key[lo], b = s_key[hi];
+        if ((a > b) == up) { s_key[lo] = b; s_key[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < k; i += blockDim.x) idx_k[i] = (long long)(s_key[i] & 0xffffffffull);
+}
+
 extern "C" int pcl_topk(const float* loss, int64_t p, int k, int64_t* idx_k, void* stream) {
   if (!loss || !idx_k || p <= 0 || k <= 0 || p > 0x7fffffffll) { pcl_set_error("bad top-k arguments"); return PCL_ERR_INVALID; }
   if (k > p) k = (int)p;
   cudaStream_t st = (cudaStream_t)stream;
+  if (p <= PCL_TOPK_SMALL) {
+    int npow2 = 2;
+    while (npow2 < (int)p) npow2 <<= 1;
+    pcl_topk_small_kernel<<<1, 1024, (size_t)npow2 * sizeof(unsigned long long), st>>>(loss, (int)p, npow2, k, (long long*)idx_k);
+    PCL_LAUNCH_CHECK();
+    return PCL_OK;
+  }
   size_t tmp_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (float*)nullptr, (float*)nullptr, (long long*)nullptr, (long long*)nullptr, (int)p, 0, 32, st);
   const size_t np = (size_t)p;

@@ -218,19 +218,24 @@ __global__ void pcl_rr_intersect_kernel(const unsigned int* __restrict__ cand_hi
 // candidate sum over cells is a block reduction.  Launch with 64 threads.
 __global__ void pcl_rr_final_kernel(const float* __restrict__ rows, const float* __restrict__ n_gt,
                                     const int K, const int nsh, const int nsw, float* __restrict__ out) {
+  extern __shared__ float s_rows[];                              // [K][2*nblk] then n_gt[nblk]: the walk below is latency-bound on every read
   __shared__ float red[2];
   const int cell = threadIdx.x, ncell = nsh * nsw, nblk = (nsh - 2) * nsw;
+  for (int i = threadIdx.x; i < K * 2 * nblk; i += blockDim.x) s_rows[i] = rows[i];
+  float* s_ngt = s_rows + (size_t)K * 2 * nblk;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) s_ngt[i] = n_gt[i];
+  __syncthreads();
   const int h = cell / nsw, w = cell - h * nsw;
   const bool compared = cell < ncell && h >= 1 && h < nsh - 1;
   float cur = 0.0f;
   for (int c = 0; c < K; ++c) {
     if (compared) {
-      const float* row = rows + (size_t)c * 2 * nblk;
+      const float* row = s_rows + (size_t)c * 2 * nblk;
       // first empty column of this row for this candidate (the `break`)
       int first_empty = nsw;
       for (int ww = 0; ww <= w; ++ww) {
         const int blk = (h - 1) * nsw + ww;
-        if (row[nblk + blk] == 0.0f || n_gt[blk] == 0.0f) { first_empty = ww; break; }
+        if (row[nblk + blk] == 0.0f || s_ngt[blk] == 0.0f) { first_empty = ww; break; }
       }
       if (w < first_empty) cur = row[(h - 1) * nsw + w];
       else if (w == first_empty) cur = 0.0f;
@@ -314,7 +319,11 @@ extern "C" int pcl_hist_rerank_finish(const float* rows_k_dev, const float* ngt_
     PCL_CUDA(cudaMemsetAsync(hist_intersect_k_dev, 0, sizeof(float) * (size_t)k, st));
     return PCL_OK;
   }
-  pcl_rr_final_kernel<<<1, 64, 0, st>>>(rows_k_dev, ngt_dev, k, num_split_h, num_split_w, hist_intersect_k_dev);
+  const int nblk_f = (num_split_h - 2) * num_split_w;
+  const size_t smem_f = ((size_t)k * 2 * nblk_f + nblk_f) * sizeof(float);
+  if (smem_f > 200 * 1024) { pcl_set_error("re-rank of %d candidates x %d blocks exceeds the finishing kernel's shared memory", k, nblk_f); return PCL_ERR_INVALID; }
+  if (smem_f > 48 * 1024) PCL_CUDA(cudaFuncSetAttribute(pcl_rr_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+  pcl_rr_final_kernel<<<1, 64, smem_f, st>>>(rows_k_dev, ngt_dev, k, num_split_h, num_split_w, hist_intersect_k_dev);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }

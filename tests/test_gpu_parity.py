@@ -204,6 +204,14 @@ def test_topk_ties_nan_and_sizes():
     big = np.round(rng.random(100003).astype(np.float32), 3)            # many ties
     np.testing.assert_array_equal(engine.topk(cu(big), 5000).cpu().numpy(), orc.topk_ascending(big, 5000))
     assert engine.topk(cu(loss[:1]), 1).cpu().tolist() == [0]
+    # both sides of the single-CTA bitonic path (<= 4096 values) / radix-sort path boundary: ties, NaN (last), -inf, negatives
+    # (no +inf: the oracle ranks NaN AS +inf, the library after it — a loss is a mean of finite residuals, never +inf)
+    for n in (2, 3, 1023, 1800, 4095, 4096, 4097):
+        v = np.round(rng.standard_normal(n).astype(np.float32), 1)
+        v[rng.random(n) < 0.03] = np.nan
+        v[rng.random(n) < 0.01] = -np.inf
+        for k in (1, min(50, n), n):
+            np.testing.assert_array_equal(engine.topk(cu(v), k).cpu().numpy(), orc.topk_ascending(v, k))
 
 
 def test_modules_autograd_contract(small):
