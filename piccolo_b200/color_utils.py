@@ -1,33 +1,17 @@
 """Per-query colour preprocessing of the reference (`color_utils.py:7-65` color_mod, `:146-234` color_match),
-SURVEY §8f next #4.  CUDA tensors are processed on the device (pcl_color.cu: histogram and rewrite passes; the
-<= 256-entry table arithmetic stays here and is shared with the numpy + cv2 restatement used for CPU tensors, which is
-pinned to the reference's golden outputs); both keep the reference's side effect that outputs are re-quantised
-through uint8."""
+SURVEY §8f next #4, on the device (pcl_color.cu: histogram and rewrite passes); only the <= 256-entry table arithmetic
+between the two passes runs here on the host.  There is no CPU path: CPU tensors and panoramas that are not uint8/255 data
+raise.  (The numpy + cv2 restatement that pins these steps to the reference's golden outputs is test infrastructure and lives
+with the other CPU restatements, outside this package.)  Both steps keep the reference's side effect that outputs are re-quantised through uint8."""
 from __future__ import annotations
 
-import cv2
 import numpy as np
 import torch
 
 
-def _lit_mask(flat: np.ndarray) -> np.ndarray:
-    """pixels whose truncated 8-bit channels do not sum to zero (`(img*255).long().sum(-1) > 0`)."""
-    return (flat * np.float32(255.0)).astype(np.int64).sum(-1) > 0
-
-
-def _to_ycc(unit_rgb: np.ndarray) -> np.ndarray:
-    u8 = (unit_rgb * np.float32(255.0)).astype(np.uint8).reshape(1, -1, 3)
-    return cv2.cvtColor(u8, cv2.COLOR_RGB2YCR_CB).reshape(-1, 3).astype(np.float32) / np.float32(255.0)
-
-
-def _to_rgb(unit_ycc: np.ndarray) -> np.ndarray:
-    u8 = (unit_ycc * np.float32(255.0)).astype(np.uint8).reshape(1, -1, 3)
-    return cv2.cvtColor(u8, cv2.COLOR_YCR_CB2RGB).reshape(-1, 3).astype(np.float32) / np.float32(255.0)
-
-
 def _equalise_cdf(hist_img: np.ndarray, hist_pts: np.ndarray) -> np.ndarray:
     """cumulative distribution of the joint luma histogram (color_utils.py:38-47): `.float()` each, add, normalise,
-    cumsum — all in fp32.  Shared by the CPU and the CUDA path."""
+    cumsum — all in fp32."""
     hist = hist_img.astype(np.float32) + hist_pts.astype(np.float32)
     return np.cumsum(hist / hist.sum(), dtype=np.float32)
 
@@ -52,23 +36,21 @@ def _color_mod_cuda(img: torch.Tensor, rgb: torch.Tensor, num_bins: int):
     return out_img, out_rgb
 
 
+
+def _require_cuda_pair(img: torch.Tensor, rgb: torch.Tensor, what: str):
+    from ._lib import PiccoloError
+    if not (isinstance(img, torch.Tensor) and isinstance(rgb, torch.Tensor) and img.is_cuda and rgb.is_cuda):
+        raise PiccoloError(f"{what} needs CUDA tensors: piccolo_b200 has no CPU path")
+
+
 def color_mod(img: torch.Tensor, rgb: torch.Tensor, num_bins: int):
     """Joint histogram equalisation of the luma of panorama and cloud (YCrCb), `sharpen_color` of the configs.
-    Returns (img (H,W,3), rgb (N,3)) float32 on img.device.  CUDA tensors are processed on the device."""
-    device = img.device
-    H, W, _ = img.shape
-    if img.is_cuda and rgb.is_cuda and 2 <= num_bins <= 4096:
-        return _color_mod_cuda(img.detach(), rgb.detach(), int(num_bins))
-    flat = img.detach().cpu().numpy().astype(np.float32).reshape(-1, 3).copy()
-    lit = _lit_mask(flat)
-    ycc_img, ycc_pts = _to_ycc(flat[lit]), _to_ycc(rgb.detach().cpu().numpy().astype(np.float32))
-    scale = np.float32(num_bins - 1)
-    bin_img, bin_pts = (ycc_img[:, 0] * scale).astype(np.int64), (ycc_pts[:, 0] * scale).astype(np.int64)
-    cdf = _equalise_cdf(np.bincount(bin_img, minlength=num_bins), np.bincount(bin_pts, minlength=num_bins))
-    ycc_img[:, 0] = cdf[bin_img]
-    ycc_pts[:, 0] = cdf[bin_pts]
-    flat[lit] = _to_rgb(ycc_img)
-    return torch.from_numpy(flat.reshape(H, W, 3)).to(device), torch.from_numpy(_to_rgb(ycc_pts)).to(rgb.device)
+    Returns (img (H,W,3), rgb (N,3)) float32 on img.device."""
+    from ._lib import PiccoloError
+    _require_cuda_pair(img, rgb, "color_mod")
+    if not 2 <= int(num_bins) <= 4096:
+        raise PiccoloError(f"color_mod: num_bins {num_bins} outside [2, 4096]")
+    return _color_mod_cuda(img.detach(), rgb.detach(), int(num_bins))
 
 
 def _interp_levels(src_counts: np.ndarray, tmp_values: np.ndarray, tmp_counts: np.ndarray, n_template: int) -> np.ndarray:
@@ -87,16 +69,6 @@ def _interp_levels(src_counts: np.ndarray, tmp_values: np.ndarray, tmp_counts: n
     small = big - 1
     out = ((src_q - xp[small]) * fp[big] + (xp[big] - src_q) * fp[small]) / (xp[big] - xp[small])
     return out.astype(np.float32)
-
-
-def _match_channel(source: np.ndarray, template: np.ndarray, weight: np.ndarray) -> np.ndarray:
-    """CDF matching of one channel (`_match_cumulative_cdf` + `_interp`), quirks kept: the source histogram is
-    indexed by truncated level `(source*255).int()`, the result is looked up by unique-value rank."""
-    _, inverse = np.unique(source, return_inverse=True)
-    tmp_values, tmp_counts = np.unique(template, return_counts=True)
-    levels = (source * np.float32(255.0)).astype(np.int32)
-    src_counts = np.bincount(levels, weights=weight.astype(np.float64)).astype(np.float32)
-    return _interp_levels(src_counts, tmp_values, tmp_counts, len(template))[inverse].reshape(source.shape)
 
 
 def _row_weight(H: int) -> np.ndarray:
@@ -150,20 +122,14 @@ def requantize(img: torch.Tensor) -> torch.Tensor:
     return table[(img * 255).to(torch.uint8).long()]
 
 
+
 def color_match(img: torch.Tensor, rgb: torch.Tensor) -> torch.Tensor:
     """Match the panorama's per-channel colour distribution (rows weighted by sin(latitude)) to the cloud's,
-    `match_color` of the configs.  Returns img (H,W,3) float32 on img.device."""
-    device = img.device
-    H, W, _ = img.shape
-    if img.is_cuda and rgb.is_cuda:
-        done = _color_match_cuda(img.detach(), rgb.detach())
-        if done is not None:
-            return done
-    weight = np.repeat(_row_weight(H), W)
-    flat = img.detach().cpu().numpy().astype(np.float32).reshape(-1, 3).copy()
-    lit = _lit_mask(flat)
-    pts = rgb.detach().cpu().numpy().astype(np.float32)
-    src = flat[lit]
-    matched = np.stack([_match_channel(src[:, c], pts[:, c], weight[lit]) for c in range(3)], axis=1)
-    flat[lit] = matched
-    return torch.from_numpy(flat.reshape(H, W, 3)).to(device)
+    `match_color` of the configs.  Returns img (H,W,3) float32 on img.device.  Both inputs must be uint8/255 data (what
+    the drivers produce, localize.py:381-414): the device path works on 256-level histograms."""
+    from ._lib import PiccoloError
+    _require_cuda_pair(img, rgb, "color_match")
+    done = _color_match_cuda(img.detach(), rgb.detach())
+    if done is None:
+        raise PiccoloError("color_match: panorama or cloud colours are not exactly uint8/255 data")
+    return done

@@ -19,5 +19,6 @@ for _ in range(10):
 torch.cuda.synchronize()
 print(f"color_match on device: {(time.perf_counter() - t0) * 100:.2f} ms per call")
 t0 = time.perf_counter()
-host = color_match(img.cpu(), rgb.cpu())
+from oracle.color_oracle import color_match_np
+host = color_match_np(img.cpu(), rgb.cpu())
 print(f"color_match CPU restatement: {(time.perf_counter() - t0) * 1e3:.1f} ms per call; identical: {bool(torch.equal(host, out.cpu()))}")

@@ -405,6 +405,7 @@ def test_color_match_on_device_matches_reference_and_host_path(golden):
     """color_match (color_utils.py:146-234) through pcl_color_stats / pcl_color_apply: against the golden output of
     the unmodified reference, and against the CPU restatement on a C4-style perturbed 1024x2048 panorama, where the
     uint8 re-quantisation the driver applies next (localize.py:404) must come out identical."""
+    from oracle.color_oracle import color_match_np
     from piccolo_b200 import _lib
     from piccolo_b200.color_utils import color_match
     g = golden("color_small")
@@ -414,7 +415,7 @@ def test_color_match_on_device_matches_reference_and_host_path(golden):
     assert m.is_cuda and _lib.launch_count() - n0 == 3                      # two statistics passes + the rewrite
     np.testing.assert_allclose(m.cpu().numpy(), g["match_img"], atol=2e-6)
     assert ((255 * m.cpu().numpy()).astype(np.uint8) != (255 * g["match_img"]).astype(np.uint8)).mean() < 1e-3
-    host = color_match(torch.from_numpy(img), torch.from_numpy(rgb)).numpy()
+    host = color_match_np(torch.from_numpy(img), torch.from_numpy(rgb)).numpy()
     np.testing.assert_array_equal(m.cpu().numpy(), host)
     # C4-sized: perturbed query panorama against a 1 M-point cloud
     room = (8.0, 6.0, 3.0)
@@ -423,7 +424,7 @@ def test_color_match_on_device_matches_reference_and_host_path(golden):
     pano8 = synth.perturb_panorama(synth.render_panorama(gt, 1024, 2048, room), seed=3, gamma=1.1, wb=(1.0, 0.97, 1.02), retexture_frac=0.1)
     img, rgb = synth.img_from_u8(pano8), synth.rgb_from_u8(rgb8)
     dev_out = color_match(cu(img), cu(rgb)).cpu().numpy()
-    host_out = color_match(torch.from_numpy(img), torch.from_numpy(rgb)).numpy()
+    host_out = color_match_np(torch.from_numpy(img), torch.from_numpy(rgb)).numpy()
     np.testing.assert_allclose(dev_out, host_out, atol=2e-7)
     np.testing.assert_array_equal((255 * dev_out).astype(np.uint8), (255 * host_out).astype(np.uint8))
     assert np.array_equal(dev_out[:64], img[:64])                           # the black caps are not lit: untouched
@@ -432,17 +433,19 @@ def test_color_match_on_device_matches_reference_and_host_path(golden):
     rq = requantize(cu(dev_out))                                            # the drivers' uint8 round trip, on the device
     np.testing.assert_array_equal(rq.cpu().numpy(), (255 * dev_out).astype(np.uint8).astype(np.float32) / np.float32(255.0))
     assert engine.Image(rq).format == engine.IMAGE_F16D                     # exactly k/255: the uint8 texel tables apply
-    # inputs that are not uint8/255 data take the CPU restatement (same result as calling it on CPU tensors)
+    # inputs that are not uint8/255 data are refused (the device path works on 256-level histograms; there is no CPU path)
     noisy = img.copy(); noisy[100, 100, 0] += 1e-3
-    a = color_match(cu(noisy), cu(rgb)).cpu().numpy()
-    b = color_match(torch.from_numpy(noisy), torch.from_numpy(rgb)).numpy()
-    np.testing.assert_array_equal(a, b)
+    with pytest.raises(_lib.PiccoloError):
+        color_match(cu(noisy), cu(rgb))
+    with pytest.raises(_lib.PiccoloError):
+        color_match(torch.from_numpy(img), torch.from_numpy(rgb))
 
 
 def test_color_mod_on_device_matches_reference_and_host_path(golden):
     """color_mod (color_utils.py:7-65) through pcl_color_mod_stats / pcl_color_mod_apply: bit-exact against the golden
     output of the unmodified reference (cv2's integer YCrCb restated in integers) and against the CPU restatement at
     full size, for 256 and 64 luma bins."""
+    from oracle.color_oracle import color_mod_np
     from piccolo_b200.color_utils import color_mod
     g = golden("color_small")
     img, rgb = synth.img_from_u8(g["img8"]), synth.rgb_from_u8(g["rgb8"])
@@ -453,6 +456,6 @@ def test_color_mod_on_device_matches_reference_and_host_path(golden):
     sc = synth.make_scene(1_000_000, 1024, 2048, seed=3)
     for bins in (256, 64):
         d_img, d_rgb = color_mod(cu(sc.img), cu(sc.rgb), bins)
-        h_img, h_rgb = color_mod(torch.from_numpy(sc.img), torch.from_numpy(sc.rgb), bins)
+        h_img, h_rgb = color_mod_np(torch.from_numpy(sc.img), torch.from_numpy(sc.rgb), bins)
         np.testing.assert_array_equal(d_img.cpu().numpy(), h_img.numpy())
         np.testing.assert_array_equal(d_rgb.cpu().numpy(), h_rgb.numpy())

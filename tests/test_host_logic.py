@@ -3,6 +3,7 @@ candidate grids, the torch make_pano used for result images."""
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from piccolo_b200 import synth
@@ -32,7 +33,9 @@ def test_configs_parse_to_reference_values():
 
 
 def test_colour_preprocessing_matches_reference(golden):
-    from piccolo_b200.color_utils import color_match, color_mod
+    """The CPU restatement (oracle/color_oracle.py: test infrastructure; the product has no CPU path) against the outputs of the
+    unmodified reference.  The device path is compared with both in tests/test_gpu_parity.py."""
+    from oracle.color_oracle import color_match_np as color_match, color_mod_np as color_mod
     g = golden("color_small")
     img = torch.from_numpy(synth.img_from_u8(g["img8"]))
     rgb = torch.from_numpy(synth.rgb_from_u8(g["rgb8"]))
@@ -167,3 +170,13 @@ def test_dataset_provider_never_ignores_dataset_keys(tmp_path, monkeypatch):
     cfg = SimpleNamespace(synthetic=True, synthetic_points=2000, synthetic_queries=1, synthetic_height=32)
     q = next(iter(datasets.queries(cfg, "Stanford2D-3D-S")))
     assert q.filename.startswith("synthetic://") and q.pcd_name.startswith("synthetic://")
+
+
+def test_colour_preprocessing_has_no_cpu_path():
+    from piccolo_b200 import _lib
+    from piccolo_b200.color_utils import color_match, color_mod
+    img, rgb = torch.zeros(4, 8, 3), torch.zeros(5, 3)
+    with pytest.raises(_lib.PiccoloError):
+        color_mod(img, rgb, 256)
+    with pytest.raises(_lib.PiccoloError):
+        color_match(img, rgb)
