@@ -327,6 +327,10 @@ _CACHE_SIZE = 8
 
 
 def _key(*tensors, extra=()):
+    """Identity of a packed handle = storage address, shape, dtype, device and torch's in-place version counter of its
+    source tensors.  Every write torch knows about (in-place ops, `copy_`, slicing assignments) bumps the counter and
+    misses the cache; a write made behind torch's back (a foreign CUDA kernel or memcpy on the raw pointer) does not —
+    call `clear_cache()` after such writes."""
     return tuple((t.data_ptr(), tuple(t.shape), t._version, str(t.device), t.dtype) for t in tensors) + tuple(extra)
 
 
