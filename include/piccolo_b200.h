@@ -188,6 +188,8 @@ int pcl_refine_read(const pcl_refine* r, float* pose_b6_dev, float* param_b6_dev
  * compute CTAs (warp 0) {cycles inside phases, cycles waiting for the next poses, phases whose poses were prefetched, 0}; the LAST row is the service CTA {cycles waiting for records, cycles reducing and stepping}.
  * Returns the number of rows recorded (0: nothing recorded) or a negative pcl_status; blocks on `stream`. */
 int pcl_refine_debug_stats(const pcl_refine* r, unsigned long long* out_host, int max_ctas, void* stream);
+/* Same option: the wall-clock stamp (ns) of the end of every iteration of the last persistent run; returns the count. */
+int pcl_refine_debug_timeline(const pcl_refine* r, unsigned long long* out_ns_host, int max_iters, void* stream);
 void pcl_refine_destroy(pcl_refine* r);
 
 /* ---- peer-memory communicator of the ranks of one box (one process per GPU) ---------------------------------- */

@@ -45,6 +45,7 @@ SIGNATURES = {
     "pcl_refine_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "pcl_refine_run_sharded": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "pcl_refine_debug_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "pcl_refine_debug_timeline": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "pcl_refine_destroy": (None, [ctypes.c_void_p]),
     "pcl_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "pcl_comm_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, c_void_pp]),

@@ -113,7 +113,7 @@ struct pcl_refine {
   size_t bc_cap;
   unsigned long long* dbg;      // option RF_DEBUG: per compute CTA cycle counters of the last persistent run
   size_t dbg_cap;
-  int dbg_ctas;
+  int dbg_ctas, dbg_iters;
 };
 
 // Peer-memory window of one rank (pcl_comm.cu): cudaMalloc'ed, IPC-mapped into every other rank of the box.

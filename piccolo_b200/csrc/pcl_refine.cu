@@ -213,9 +213,9 @@ static int pcl_refine_run_fused(pcl_refine* r, const pcl_cloud* c, const pcl_ima
       PCL_CUDA(e);
       ps.bc = r->bc_dev;
       if (pcl_opt(PCL_OPT_RF_DEBUG)) {
-        rc = pcl_rf_grow((void**)&r->dbg, &r->dbg_cap, (size_t)(G + 1) * 4, sizeof(unsigned long long), st);
+        rc = pcl_rf_grow((void**)&r->dbg, &r->dbg_cap, (size_t)(G + 1) * 4 + (size_t)num_iter, sizeof(unsigned long long), st);   // CTA rows, then one wall-clock stamp per iteration
         if (rc) return rc;
-        ps.dbg = r->dbg; r->dbg_ctas = (int)G + 1;
+        ps.dbg = r->dbg; r->dbg_ctas = (int)G + 1; r->dbg_iters = num_iter;
       }
       e = pcl_rf_dispatch_persistent(view.fmt, ps, st);
       if (e == cudaSuccess) {
@@ -294,6 +294,17 @@ extern "C" int pcl_refine_debug_stats(const pcl_refine* r, unsigned long long* o
   if (!r->dbg || r->dbg_ctas <= 0) return 0;
   const int n = r->dbg_ctas < max_ctas ? r->dbg_ctas : max_ctas;
   PCL_CUDA(cudaMemcpyAsync(out_host, r->dbg, sizeof(unsigned long long) * 4 * (size_t)n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  PCL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return n;
+}
+
+// Option RF_DEBUG: the service CTA's wall-clock stamp (%globaltimer, ns) at the end of every iteration of the last persistent
+// run.  Returns the number of iterations copied (0 when nothing was recorded).  Blocks on `stream`.
+extern "C" int pcl_refine_debug_timeline(const pcl_refine* r, unsigned long long* out_ns_host, int max_iters, void* stream) {
+  if (!r || !out_ns_host) { pcl_set_error("null refine handle or output"); return PCL_ERR_INVALID; }
+  if (!r->dbg || r->dbg_ctas <= 0 || r->dbg_iters <= 0) return 0;
+  const int n = r->dbg_iters < max_iters ? r->dbg_iters : max_iters;
+  PCL_CUDA(cudaMemcpyAsync(out_ns_host, r->dbg + 4 * (size_t)r->dbg_ctas, sizeof(unsigned long long) * (size_t)n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   PCL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return n;
 }

@@ -445,7 +445,14 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
         if (tid == 0) {                                            // release is cumulative over the barrier above; no fence:
           const unsigned int v = ps.ready_base[b] + (unsigned int)(it + 1);   // a gpu-scope fence would also invalidate this SM's L1
           asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ps.ready + b), "r"(v) : "memory");
-          if (ps.dbg) { sv_wait += s1 - s0; sv_work += clock64() - s1; }
+          if (ps.dbg) {
+            sv_wait += s1 - s0; sv_work += clock64() - s1;
+            if (b == ps.nblk - 1) {                              // end of iteration `it`: wall clock [ns] for the per-iteration timeline
+              unsigned long long tns;
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+              ps.dbg[4 * (size_t)(G + 1) + it] = tns;
+            }
+          }
         }
       }
     }

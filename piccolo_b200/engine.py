@@ -254,6 +254,16 @@ class Refiner:
             _lib.check(n)
         return buf[:n]
 
+    def debug_timeline(self):
+        """Option RF_DEBUG: wall-clock stamps (ns, uint64 numpy array) of the end of every iteration of the last persistent run."""
+        import numpy as np
+        buf = np.zeros(4096, dtype=np.uint64)
+        with torch.cuda.device(self.device):
+            n = _lib.load().pcl_refine_debug_timeline(self._h, buf.ctypes.data, 4096, _stream(self.device))
+        if n < 0:
+            _lib.check(n)
+        return buf[:n]
+
     def read(self):
         """Returns dict(pose (B,6), param (B,6), loss (B,), lr (B,) float64) on the device."""
         dev = self.device
