@@ -95,13 +95,20 @@ def localize_query(cloud: engine.Cloud, image: engine.Image, grid: torch.Tensor,
 
 def localize_query_host(xyz_h: torch.Tensor, rgb_h: torch.Tensor, img_h: torch.Tensor, grid_h, cfg, device):
     """End-to-end call with HOST (pinned) buffers: upload, pack, score, refine, and read the answer back.
-    Returns (pose (6,) cpu, loss cpu float)."""
+    Returns (pose (6,) cpu, loss cpu float).  The panorama travels on the upload stream while the cloud is packed
+    (Morton sort, clamp box) on the current one; the two join before scoring."""
+    main, side = torch.cuda.current_stream(device), _side_stream(device)
     xyz = xyz_h.to(device, non_blocking=True)
     rgb = rgb_h.to(device, non_blocking=True)
-    img = img_h.to(device, non_blocking=True)
     grid = grid_h.to(device, non_blocking=True)          # (P,6) tensor or StartGrid
-    cloud = engine.Cloud(xyz, rgb, cfg.out_of_room_quantile)
-    image = engine.Image(img)
+    copied = main.record_event()
+    cloud = engine.Cloud(xyz, rgb, cfg.out_of_room_quantile)      # enqueued first: Image() below waits on the host for one word
+    side.wait_event(copied)                              # copies share the link: the panorama queues behind the cloud's arrays
+    with torch.cuda.stream(side):
+        img = img_h.to(device, non_blocking=True)
+        img.record_stream(main)
+        image = engine.Image(img)
+    main.wait_stream(side)
     out = localize_query(cloud, image, grid, cfg, img=img)
     res = torch.cat([out["pose"], out["loss"].reshape(1)]).cpu()
     return res[:6], float(res[6])
