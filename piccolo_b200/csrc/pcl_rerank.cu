@@ -167,13 +167,35 @@ __global__ void __launch_bounds__(256) pcl_rr_cand_hist_kernel(const float* __re
   const unsigned long long* kimg = keys + (size_t)cand * (size_t)(ky_hi - ky_lo) * (size_t)W;
   const int y0 = h * bh + strip * PCL_RR_STRIP, y1 = min(y0 + PCL_RR_STRIP, (h + 1) * bh);
   for (int y = y0; y < y1; ++y) {
+    const bool row_interior = y > 0 && y < H - 1;
+    // the three key rows around y (64-bit words as uint2: .y holds the presence bit, .x the lit flag and the colour bin)
+    const uint2* kr = reinterpret_cast<const uint2*>(kimg + (size_t)(y - ky_lo) * W);
+    const float* irow = img + (size_t)y * W * 3;
     for (int xo = threadIdx.x; xo < bw; xo += blockDim.x) {
       const int x = w * bw + xo;
-      const float* px = img + ((size_t)y * W + x) * 3;
-      const float i0 = px[0], i1 = px[1], i2 = px[2];            // independent of the keys: in flight together with them
-      const unsigned long long key = pcl_rr_winner(kimg, H, W, ky_lo, y, x);
+      const float i0 = irow[3 * x], i1 = irow[3 * x + 1], i2 = irow[3 * x + 2];   // independent of the keys: in flight together with them
+      unsigned int low;
+      if (row_interior && x > 0 && x < W - 1) {
+        // interior pixel: exactly one source per call.  Nine independent loads at constant offsets from one address;
+        // source of call (dy, dx) is (y - dy, x - dx); priority = reverse call order: centre, idx1 (+1,+1), idx2 (+1,0),
+        // idx3 (+1,-1), idx4 (-1,+1), idx5 (-1,0), idx6 (-1,-1), idx7 (0,+1), idx8 (0,-1).  The first source that holds a
+        // key decides; only its low word (lit flag + bin) is needed.
+        const uint2* c = kr + x;
+        const uint2 k0 = c[0], k1 = c[-W - 1], k2 = c[-W], k3 = c[-W + 1], k4 = c[W - 1], k5 = c[W], k6 = c[W + 1], k7 = c[-1], k8 = c[1];
+        low = k8.y ? k8.x : 0u;
+        low = k7.y ? k7.x : low;
+        low = k6.y ? k6.x : low;
+        low = k5.y ? k5.x : low;
+        low = k4.y ? k4.x : low;
+        low = k3.y ? k3.x : low;
+        low = k2.y ? k2.x : low;
+        low = k1.y ? k1.x : low;
+        low = k0.y ? k0.x : low;
+      } else {
+        low = (unsigned int)pcl_rr_winner(kimg, H, W, ky_lo, y, x);        // 0 when no source holds a key
+      }
       const bool img_lit = !(i0 * 255.0f == 0.0f && i1 * 255.0f == 0.0f && i2 * 255.0f == 0.0f);       // img_mask
-      if (key != 0ull && img_lit && ((key >> 9) & 1ull)) atomicAdd(&hist[(unsigned int)key & 511u], 1u);
+      if (img_lit && ((low >> 9) & 1u)) atomicAdd(&hist[low & 511u], 1u);
     }
   }
   __syncthreads();
