@@ -237,38 +237,42 @@ __global__ void pcl_rr_intersect_kernel(const unsigned int* __restrict__ cand_hi
 // The reference's loop, quirks included (utils.py:547-579): the split table persists across candidates, an empty
 // block writes 0 and BREAKS the inner (column) loop (cells to its right keep the previous candidate's value),
 // NaN -> 0, mean over ALL nsh*nsw cells.  One thread per table cell walks the candidates in order; the per-
-// candidate sum over cells is a block reduction.  Launch with 64 threads.
+// candidate sum over cells is a warp reduction.  Launch with 32 threads.
 __global__ void pcl_rr_final_kernel(const float* __restrict__ rows, const float* __restrict__ n_gt,
                                     const int K, const int nsh, const int nsw, float* __restrict__ out) {
-  extern __shared__ float s_rows[];                              // [K][2*nblk] then n_gt[nblk]: the walk below is latency-bound on every read
-  __shared__ float red[2];
-  const int cell = threadIdx.x, ncell = nsh * nsw, nblk = (nsh - 2) * nsw;
-  for (int i = threadIdx.x; i < K * 2 * nblk; i += blockDim.x) s_rows[i] = rows[i];
+  // ONE warp, two table cells per lane (nsh*nsw <= 64): the walk over the candidates is sequential by construction, so it
+  // runs without block barriers; the rows sit in shared memory because every read is on the critical path
+  extern __shared__ float s_rows[];                              // [K][2*nblk] then n_gt[nblk]
+  const int lane = threadIdx.x, ncell = nsh * nsw, nblk = (nsh - 2) * nsw;
+  for (int i = lane; i < K * 2 * nblk; i += 32) s_rows[i] = rows[i];
   float* s_ngt = s_rows + (size_t)K * 2 * nblk;
-  for (int i = threadIdx.x; i < nblk; i += blockDim.x) s_ngt[i] = n_gt[i];
-  __syncthreads();
-  const int h = cell / nsw, w = cell - h * nsw;
-  const bool compared = cell < ncell && h >= 1 && h < nsh - 1;
-  float cur = 0.0f;
+  for (int i = lane; i < nblk; i += 32) s_ngt[i] = n_gt[i];
+  __syncwarp();
+  float cur[2] = {0.0f, 0.0f};
   for (int c = 0; c < K; ++c) {
-    if (compared) {
-      const float* row = s_rows + (size_t)c * 2 * nblk;
-      // first empty column of this row for this candidate (the `break`)
-      int first_empty = nsw;
-      for (int ww = 0; ww <= w; ++ww) {
-        const int blk = (h - 1) * nsw + ww;
-        if (row[nblk + blk] == 0.0f || s_ngt[blk] == 0.0f) { first_empty = ww; break; }
+    const float* row = s_rows + (size_t)c * 2 * nblk;
+    float s = 0.0f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int cell = lane + 32 * half;
+      const int h = cell / nsw, w = cell - h * nsw;
+      if (cell < ncell && h >= 1 && h < nsh - 1) {
+        // first empty column of this row for this candidate (the `break`)
+        int first_empty = nsw;
+        for (int ww = 0; ww <= w; ++ww) {
+          const int blk = (h - 1) * nsw + ww;
+          if (row[nblk + blk] == 0.0f || s_ngt[blk] == 0.0f) { first_empty = ww; break; }
+        }
+        if (w < first_empty) cur[half] = row[(h - 1) * nsw + w];
+        else if (w == first_empty) cur[half] = 0.0f;
+        if (isnan(cur[half])) cur[half] = 0.0f;
       }
-      if (w < first_empty) cur = row[(h - 1) * nsw + w];
-      else if (w == first_empty) cur = 0.0f;
-      if (isnan(cur)) cur = 0.0f;
     }
-    float s = (cell < ncell) ? cur : 0.0f;
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) out[c] = (red[0] + red[1]) / (float)ncell;
-    __syncthreads();
+    // the sum over the cells in the order of the 64-thread version (two warp sums of 32 cells, then their sum)
+    float s0 = (lane < ncell) ? cur[0] : 0.0f, s1 = (lane + 32 < ncell) ? cur[1] : 0.0f;
+    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    s = s0 + s1;
+    if (lane == 0) out[c] = s / (float)ncell;
   }
 }
 
@@ -345,7 +349,7 @@ extern "C" int pcl_hist_rerank_finish(const float* rows_k_dev, const float* ngt_
   const size_t smem_f = ((size_t)k * 2 * nblk_f + nblk_f) * sizeof(float);
   if (smem_f > 200 * 1024) { pcl_set_error("re-rank of %d candidates x %d blocks exceeds the finishing kernel's shared memory", k, nblk_f); return PCL_ERR_INVALID; }
   if (smem_f > 48 * 1024) PCL_CUDA(cudaFuncSetAttribute(pcl_rr_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-  pcl_rr_final_kernel<<<1, 64, smem_f, st>>>(rows_k_dev, ngt_dev, k, num_split_h, num_split_w, hist_intersect_k_dev);
+  pcl_rr_final_kernel<<<1, 32, smem_f, st>>>(rows_k_dev, ngt_dev, k, num_split_h, num_split_w, hist_intersect_k_dev);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }
