@@ -147,9 +147,9 @@ static int pcl_refine_run_fused(pcl_refine* r, const pcl_cloud* c, const pcl_ima
   bool fully_resident = false;
   {
     // points a CTA keeps in shared memory for the whole run: its whole range when that fits beside the kernel's static
-    // arrays (<= ~8.6 k points per CTA = 1.27 M points per GPU), whole 2048-point groups of it for clouds up to 3x that
-    // size, nothing beyond (the resident share is small there and the texel gather makes better use of the unified
-    // shared-memory/L1 array).  Option RF_RES: -1/1 = this rule, 0 = off.
+    // arrays with >= 60 KB left as L1 (14 rows of 512 points = 1.05 M points per GPU), else whole 2048-point groups of it
+    // (measured: 3 M points 125 -> 120 us per iteration, 5 M 206 -> 201, 10 M 399 -> 396; the rest streams evict-first).
+    // Option RF_RES: -1/1 = this rule, 0 = off.
     int dev = 0, optin = 0;
     PCL_CUDA(cudaGetDevice(&dev));
     PCL_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -158,7 +158,7 @@ static int pcl_refine_run_fused(pcl_refine* r, const pcl_cloud* c, const pcl_ima
     const long long budget = (long long)(optin < 196 * 1024 ? optin : 196 * 1024) - PCL_RF_SMEM_STATIC;
     const long long cap = budget / (PCL_RF_ROWF * (long long)sizeof(float)) * PCL_RF_THREADS;   // whole rows of 512 points
     const long long per_cta = (n_pts + G - 1) / G;
-    long long res = per_cta <= cap ? per_cta : (per_cta <= 3 * cap ? cap / PCL_RF_GROUP * PCL_RF_GROUP : 0);
+    long long res = per_cta <= cap ? per_cta : cap / PCL_RF_GROUP * PCL_RF_GROUP;
     if (pcl_opt(PCL_OPT_RF_RES) == 0 || cap <= 0) res = 0;
     fully_resident = res > 0 && res >= per_cta;
     ps.res_pts = (int)res;
