@@ -63,3 +63,26 @@ def test_option_names_are_validated():
     from piccolo_b200 import _lib
     with pytest.raises(_lib.PiccoloError):
         _lib.set_option("NO_SUCH_KNOB", 1)
+
+
+def test_partly_resident_cloud_equals_per_iteration_bitwise():
+    """A cloud too large to keep whole in shared memory (1.3 M points: 3 of its 4.3 groups per CTA resident, the rest streamed
+    evict-first) and one streamed entirely (option RF_RES=0) must give the same bits as the per-iteration launches, which read
+    everything from global memory."""
+    from piccolo_b200 import _lib, engine, synth
+    dev = torch.device("cuda:0")
+    sc = synth.make_scene(1_300_003, 256, 512, seed=4)
+    xyz, rgb, img = [torch.from_numpy(a).to(dev) for a in (sc.xyz, sc.rgb, sc.img)]
+    cloud, image = engine.Cloud(xyz, rgb), engine.Image(img)
+    rng = np.random.default_rng(1)
+    starts = torch.from_numpy(np.stack([sc.gt_pose + np.concatenate([rng.normal(0, 0.3, 3), rng.normal(0, 0.2, 3)]) for _ in range(6)]).astype(np.float32)).to(dev)
+    a = _run(cloud, image, starts, 6, True, 1, (12,))
+    b = _run(cloud, image, starts, 6, True, 0, (12,))
+    _lib.set_option("RF_RES", 0)
+    try:
+        c = _run(cloud, image, starts, 6, True, 1, (12,))
+    finally:
+        _lib.set_option("RF_RES", -1)
+    for x, y, z in zip(a, b, c):
+        assert np.array_equal(x, y, equal_nan=True) and np.array_equal(x, z, equal_nan=True)
+    assert np.isfinite(a[2]).all()
