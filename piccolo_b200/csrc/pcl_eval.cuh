@@ -513,18 +513,20 @@ PCL_HD void pcl_grid_member(const PclImage& I, const PclGridBase& b, float delta
 // ---------------------------------------------------------------------------------------------
 // pose set-up and gradient finish (one thread per pose)
 // ---------------------------------------------------------------------------------------------
-PCL_HD void pcl_pose_from_params(const float* p6, PclPose& P) {
-  // R = (Rz·Ry)·Rx in fp32 like the reference's two torch.mm calls (omniloc.py:187-188)
-  const float cy = cosf(p6[3]), sy = sinf(p6[3]);
-  const float cp = cosf(p6[4]), sp = sinf(p6[4]);
-  const float cr = cosf(p6[5]), sr = sinf(p6[5]);
+// R = (Rz·Ry)·Rx in fp32 like the reference's two torch.mm calls (omniloc.py:187-188), from the six trigonometric values
+PCL_HD void pcl_pose_from_trig(const float cy, const float sy, const float cp, const float sp, const float cr, const float sr,
+                               const float tx, const float ty, const float tz, PclPose& P) {
   const float m00 = cy * cp, m01 = -sy, m02 = cy * sp;
   const float m10 = sy * cp, m11 = cy, m12 = sy * sp;
   const float m20 = -sp, m21 = 0.0f, m22 = cp;
   P.r00 = m00; P.r01 = m01 * cr + m02 * sr; P.r02 = m02 * cr - m01 * sr;
   P.r10 = m10; P.r11 = m11 * cr + m12 * sr; P.r12 = m12 * cr - m11 * sr;
   P.r20 = m20; P.r21 = m21 * cr + m22 * sr; P.r22 = m22 * cr - m21 * sr;
-  P.tx = p6[0]; P.ty = p6[1]; P.tz = p6[2];
+  P.tx = tx; P.ty = ty; P.tz = tz;
+}
+
+PCL_HD void pcl_pose_from_params(const float* p6, PclPose& P) {
+  pcl_pose_from_trig(cosf(p6[3]), sinf(p6[3]), cosf(p6[4]), sinf(p6[4]), cosf(p6[5]), sinf(p6[5]), p6[0], p6[1], p6[2], P);
 }
 
 // sums[8] = {Σ m e, Σ m, a(3), τ(3)} (already reduced over all points)  ->  loss, grad[6]

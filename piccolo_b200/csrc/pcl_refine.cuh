@@ -314,39 +314,48 @@ struct PclRfConsts {
   int patience, batch_semantics;
 };
 
-// Every thread of the CTA: deterministic two-level fp64 reduction of the block's n_rec records (slot stride
-// MAXNPB*8 doubles), then one thread per (candidate, parameter): loss + analytic gradient + torch.optim.Adam
+// Every thread of the CTA: deterministic fp64 reduction of the block's n_rec records (slot stride MAXNPB*8 doubles; one warp
+// per pair of sums), then one thread per (candidate, parameter): loss + analytic gradient + torch.optim.Adam
 // (single-tensor path, betas 0.9/0.999, eps 1e-8; fp32 tensors, fp64 python scalars) + ReduceLROnPlateau(mode=min,
 // threshold 1e-4 rel, cooldown 0, min_lr 0, eps 1e-8) + translation clamp, exactly the split torch has
 // (omniloc.py:33,37,49-58).  st/evalp/pose are the block's np entries (shared or global memory).
 // Contains __syncthreads: call from all threads.  On return evalp/pose hold the next iteration's pose.
 __device__ __forceinline__ void pcl_rf_finalize(const double* __restrict__ rec, const int n_rec, const int np, double2* __restrict__ s_sum,
                                                 PclRefineState* __restrict__ st, float* __restrict__ evalp, PclPose* __restrict__ pose,
-                                                const PclImage& I, const PclRfConsts& k, const double bc1, const double bc2_sqrt, const int tid) {
-  const int nitems = np * (PCL_NSUM / 2);                        // 16-byte pairs of sums
-  const int GG = PCL_RF_THREADS / nitems;
+                                                const PclImage& I, const PclRfConsts& k, const double bc1, const double bc2_sqrt, const int tid,
+                                                long long* dbg_split = nullptr) {
+  const long long f0 = dbg_split ? clock64() : 0;
+  const int nitems = np * (PCL_NSUM / 2);                        // 16-byte pairs of sums: at most 16 = one per warp
+  // the clamp box of the parameter thread, issued now and consumed at the very end of the optimiser step
+  float box_lo = 0.0f, box_hi = 0.0f;
+  if (tid < 32 && (tid % 6) < 3) { box_lo = __ldg(k.box + tid % 6); box_hi = __ldg(k.box + 3 + tid % 6); }
   {
-    const int item = tid % nitems, g = tid / nitems;
-    double2 t = make_double2(0.0, 0.0);
-    if (g < GG) {
-      const double2* src = reinterpret_cast<const double2*>(rec) + item;
+    // warp w reduces item w: lane l adds records l, l + 32, ... in order, then a 5-step xor tree (every lane ends with the
+    // same bits: each step adds the same two partial sums on both sides) — one L2 round trip, no shared-memory chain
+    const int lane = tid & 31, warp = tid >> 5;
+    if (warp < nitems) {
+      const double2* src = reinterpret_cast<const double2*>(rec) + warp;
       constexpr int stride = PCL_RF_MAXNPB * PCL_NSUM / 2;
-#pragma unroll 8
-      for (int s = g; s < n_rec; s += GG) {
-        const double2 v = __ldcg(src + (size_t)s * stride);
-        t.x += v.x; t.y += v.y;
+      double2 t = make_double2(0.0, 0.0);
+      // eight records per lane per round, all eight loads in flight before the first add (one L2 round trip per 256
+      // records: the single-GPU case is one round)
+      for (int s0 = lane; s0 < n_rec; s0 += 256) {
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int s = s0 + 32 * u;
+          v[u] = s < n_rec ? __ldcg(src + (size_t)s * stride) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { t.x += v[u].x; t.y += v[u].y; }
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { t.x += __shfl_xor_sync(0xffffffffu, t.x, o); t.y += __shfl_xor_sync(0xffffffffu, t.y, o); }
+      if (lane == 0) s_sum[warp] = t;
     }
-    s_sum[tid] = t;
   }
   __syncthreads();
-  double2 tot = make_double2(0.0, 0.0);
-  if (tid < nitems) {
-    for (int g = 0; g < GG; ++g) { const double2 v = s_sum[g * nitems + tid]; tot.x += v.x; tot.y += v.y; }
-  }
-  __syncthreads();
-  if (tid < nitems) s_sum[tid] = tot;
-  __syncthreads();
+  if (dbg_split) dbg_split[0] += clock64() - f0;                 // records reduced
   if (tid < 32) {
     const int p = tid / 6, i = tid - 6 * p;
     const bool act = tid < np * 6;
@@ -386,11 +395,15 @@ __device__ __forceinline__ void pcl_rf_finalize(const double* __restrict__ rec, 
       }
       // clamp the translation into the quantile box; batch semantics evaluates the pre-clamp copy next (omniloc.py:260-269)
       float c = newp;
-      if (i < 3) c = fminf(fmaxf(c, __ldg(k.box + i)), __ldg(k.box + 3 + i));
+      if (i < 3) c = fminf(fmaxf(c, box_lo), box_hi);
       S.param[i] = c;
-      evalp[6 * p + i] = k.batch_semantics ? newp : c;
+      const float ev = k.batch_semantics ? newp : c;
+      evalp[6 * p + i] = ev;
+      // the next pose: the three angle threads take cos/sin of their own angle, the first thread assembles R
+      float* trig = reinterpret_cast<float*>(s_sum + 32) + 8 * p;  // scratch behind the 16 sums
+      if (i >= 3) { trig[2 * (i - 3)] = cosf(ev); trig[2 * (i - 3) + 1] = sinf(ev); }
       __syncwarp(mask);
-      if (i == 0) pcl_pose_from_params(evalp + 6 * p, pose[p]);
+      if (i == 0) pcl_pose_from_trig(trig[0], trig[1], trig[2], trig[3], trig[4], trig[5], evalp[6 * p], evalp[6 * p + 1], evalp[6 * p + 2], pose[p]);
     }
   }
   __syncthreads();
@@ -428,7 +441,7 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
       pcl_pose_from_params(s_evalp[tid], s_pose[0][tid]);
     }
     __syncthreads();
-    long long sv_wait = 0, sv_work = 0;
+    long long sv_wait = 0, sv_work = 0, sv_reduce = 0;
     for (int it = 0; it < ps.num_iter; ++it) {
       for (int b = 0; b < ps.nblk; ++b) {
         const int p0 = b * ps.npb, np = min(ps.npb, ps.B - p0);
@@ -439,7 +452,7 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
         // records are double-buffered by iteration parity: a fast rank's next record must not overwrite the copy a slower
         // rank's service CTA is still reading
         pcl_rf_finalize(ps.rec[ps.rank] + ((size_t)((ps.parity0 + it) & 1) * ps.nblk + b) * rec_blk, n_rec, np, s_sum, s_state + p0, &s_evalp[p0][0], &s_pose[0][p0], ps.I, k,
-                        __ldg(ps.bc + 2 * it), __ldg(ps.bc + 2 * it + 1), tid);
+                        __ldg(ps.bc + 2 * it), __ldg(ps.bc + 2 * it + 1), tid, ps.dbg ? &sv_reduce : nullptr);
         if (tid < np * 12) ps.posebuf[(size_t)p0 * 12 + tid] = reinterpret_cast<const float*>(&s_pose[0][p0])[tid];
         __syncthreads();
         if (tid == 0) {                                            // release is cumulative over the barrier above; no fence:
@@ -456,7 +469,7 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
         }
       }
     }
-    if (ps.dbg && tid == 0) { ps.dbg[4 * (size_t)G] = (unsigned long long)sv_wait; ps.dbg[4 * (size_t)G + 1] = (unsigned long long)sv_work; ps.dbg[4 * (size_t)G + 2] = 0; ps.dbg[4 * (size_t)G + 3] = 0; }
+    if (ps.dbg && tid == 0) { ps.dbg[4 * (size_t)G] = (unsigned long long)sv_wait; ps.dbg[4 * (size_t)G + 1] = (unsigned long long)sv_work; ps.dbg[4 * (size_t)G + 2] = (unsigned long long)sv_reduce; ps.dbg[4 * (size_t)G + 3] = 0; }
     if (tid < ps.B) {                                            // the end state
       ps.state[tid] = s_state[tid];
 #pragma unroll

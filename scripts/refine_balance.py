@@ -22,7 +22,7 @@ run(); torch.cuda.synchronize()
 st = ref.debug_stats().astype(np.float64)          # (ctas + 1, 4), last row = service CTA
 sv, st = st[-1], st[:-1]
 busy, wait = st[:, 0] / 100, st[:, 1] / 100
-print(f"service CTA per iteration: waiting for records {sv[0]/100:.0f} cycles, reducing + stepping {sv[1]/100:.0f} cycles | compute warp 0: phases with prefetched "
+print(f"service CTA per iteration: waiting for records {sv[0]/100:.0f} cycles, reducing + stepping {sv[1]/100:.0f} cycles (of which reducing the records {sv[2]/100:.0f}) | compute warp 0: phases with prefetched "
       f"poses {st[:,2].mean():.0f} of 200 (min {st[:,2].min():.0f}))")
 print(f"{ms*10:.2f} us/iter | per-CTA busy cycles/iter: mean {busy.mean():.0f} min {busy.min():.0f} p5 {np.percentile(busy,5):.0f} p50 {np.median(busy):.0f} "
       f"p95 {np.percentile(busy,95):.0f} max {busy.max():.0f} | wait cycles/iter: mean {wait.mean():.0f} min {wait.min():.0f} max {wait.max():.0f}", flush=True)
