@@ -79,7 +79,6 @@ def _row_weight(H: int) -> np.ndarray:
 def _color_match_cuda(img: torch.Tensor, rgb: torch.Tensor):
     """CUDA path (pcl_color.cu): three 256-bin histograms per side on the device, the <= 256-entry interpolation
     here, one rewrite pass on the device.  Returns None when an input is not exactly uint8/255 data."""
-    import ctypes
     from . import _lib
     from .engine import _f32c, _stream
     lib = _lib.load()
