@@ -107,7 +107,7 @@ struct pcl_refine {
   unsigned int arrive_base[8];  // their current values (host copy; a run advances the counters of ITS pose blocks only)
   unsigned int* ready;          // [PCL_RF_MAXBLK] monotonic "poses published" flags of the service CTA
   unsigned int ready_base[8];
-  float* posebuf;               // [min(B,16)][12] published poses
+  unsigned long long* posebuf;  // [min(B,16)][12] published poses as {tag : 32 | float bits : 32} words
   unsigned int* tickets;        // [PCL_RF_MAXBLK] last-block-done tickets of the per-iteration fallback
   double* bc_dev;               // grow-only: per-iteration Adam bias corrections of a persistent run, [num_iter][2]
   size_t bc_cap;

@@ -58,7 +58,7 @@ extern "C" int pcl_refine_reset(pcl_refine* r, const float* poses_b6_dev, void* 
   const size_t o_ready = o_arr + 256;
   const size_t o_tick = o_ready + 256;
   const size_t o_pose = o_tick + 256;
-  const size_t total = o_pose + sizeof(float) * 12 * PCL_RF_MAXB;
+  const size_t total = o_pose + sizeof(unsigned long long) * 12 * PCL_RF_MAXB;
   if (!r->block) {
     PCL_CUDA(pcl_pool_alloc((void**)&r->block, total, st));
     r->owner = st;
@@ -69,7 +69,7 @@ extern "C" int pcl_refine_reset(pcl_refine* r, const float* poses_b6_dev, void* 
     r->arrive = (unsigned int*)(r->block + o_arr);
     r->ready = (unsigned int*)(r->block + o_ready);
     r->tickets = (unsigned int*)(r->block + o_tick);
-    r->posebuf = (float*)(r->block + o_pose);
+    r->posebuf = (unsigned long long*)(r->block + o_pose);
     PCL_CUDA(cudaMemsetAsync(r->block + o_cnt, 0, total - o_cnt, st));    // tickets are self-resetting, arrivals / ready flags monotonic
     memset(r->arrive_base, 0, sizeof(r->arrive_base));
     memset(r->ready_base, 0, sizeof(r->ready_base));
@@ -188,7 +188,7 @@ static int pcl_refine_run_fused(pcl_refine* r, const pcl_cloud* c, const pcl_ima
     memcpy(ps.arrive_base, r->arrive_base, sizeof(ps.arrive_base));
   }
   ps.parity0 = (int)(r->steps_done & 1);
-  ps.ready = r->ready; ps.posebuf = r->posebuf;
+  ps.posebuf = r->posebuf;
   memcpy(ps.ready_base, r->ready_base, sizeof(ps.ready_base));
 
   if (num_iter >= 1 && (comm || pcl_opt(PCL_OPT_PERSIST) != 0)) {

@@ -56,9 +56,9 @@ struct PclRfParams {
   unsigned int* arrive[PCL_RF_MAXRANKS];  // arrival counters of all ranks: [nblk], monotonic
   unsigned int arrive_base[PCL_RF_MAXBLK];   // value of block b's counter when this run starts
   int parity0;                  // record parity of this run's first iteration (records are double-buffered by iteration parity)
-  unsigned int* ready;          // [nblk] local: ready[b] - ready_base[b] = iterations of block b whose poses are published
-  unsigned int ready_base[PCL_RF_MAXBLK];
-  float* posebuf;               // [B][12] local: PclPose of every candidate for its next phase (valid behind `ready`)
+  unsigned int ready_base[PCL_RF_MAXBLK];   // tag base of block b: the poses for iteration `it` carry tag ready_base[b] + it
+  unsigned long long* posebuf;  // [B][12] local: PclPose of every candidate for its next phase as self-validating 64-bit
+                                // words {tag : 32 | float bits : 32} (a 64-bit store is single-copy atomic: no flag, no fence)
   const double* bc;             // [num_iter][2] = {1 - 0.9^step, sqrt(1 - 0.999^step)} (host libm, as python's `beta ** step`)
   int num_iter;
   PclRefineState* state;        // [B] global
@@ -82,6 +82,16 @@ __device__ __forceinline__ unsigned int pcl_ld_poll_sys(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+
+// 64-bit pose words {tag : 32 | float bits : 32}: relaxed accesses served by L2; a word validates itself through its tag
+__device__ __forceinline__ unsigned long long pcl_ld_word_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void pcl_st_word_gpu(unsigned long long* p, const unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // Warp reduction of 8 values with a halving butterfly (7 + 2 shuffles instead of 40).  On return lane L with
@@ -453,11 +463,13 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
         // rank's service CTA is still reading
         pcl_rf_finalize(ps.rec[ps.rank] + ((size_t)((ps.parity0 + it) & 1) * ps.nblk + b) * rec_blk, n_rec, np, s_sum, s_state + p0, &s_evalp[p0][0], &s_pose[0][p0], ps.I, k,
                         __ldg(ps.bc + 2 * it), __ldg(ps.bc + 2 * it + 1), tid, ps.dbg ? &sv_reduce : nullptr);
-        if (tid < np * 12) ps.posebuf[(size_t)p0 * 12 + tid] = reinterpret_cast<const float*>(&s_pose[0][p0])[tid];
-        __syncthreads();
-        if (tid == 0) {                                            // release is cumulative over the barrier above; no fence:
-          const unsigned int v = ps.ready_base[b] + (unsigned int)(it + 1);   // a gpu-scope fence would also invalidate this SM's L1
-          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ps.ready + b), "r"(v) : "memory");
+        // publish: every float of the block's poses travels with the tag of the iteration it is for, in one 64-bit store
+        // (single-copy atomic) — no flag, no release, no second round trip on the reader's side
+        if (tid < np * 12) {
+          const unsigned long long tag = (unsigned long long)(ps.ready_base[b] + (unsigned int)(it + 1));
+          pcl_st_word_gpu(ps.posebuf + (size_t)p0 * 12 + tid, (tag << 32) | (unsigned long long)__float_as_uint(reinterpret_cast<const float*>(&s_pose[0][p0])[tid]));
+        }
+        if (tid == 0) {
           if (ps.dbg) {
             sv_wait += s1 - s0; sv_work += clock64() - s1;
             if (b == ps.nblk - 1) {                              // end of iteration `it`: wall clock [ns] for the per-iteration timeline
@@ -516,21 +528,27 @@ __global__ void __launch_bounds__(PCL_RF_THREADS, PCL_RF_CTAS_PER_SM) pcl_refine
       } else if (s_pref[buf] == ph) {
         n_hit += 1;
       } else {                                                   // not prefetched (uniform: written before the last barrier)
-        if (tid == 0) pcl_rf_spin(ps.ready + b, ps.ready_base[b] + (unsigned int)it, false, 0u);
-        __syncthreads();
-        if (tid < np * 12) reinterpret_cast<float*>(&s_pose[buf][0])[tid] = __ldcg(ps.posebuf + (size_t)p0 * 12 + tid);
+        if (tid < np * 12) {                                     // every word is polled by the thread that needs it: one L2 round trip
+          const unsigned int want = ps.ready_base[b] + (unsigned int)it;
+          unsigned long long w;
+          do { w = pcl_ld_word_gpu(ps.posebuf + (size_t)p0 * 12 + tid); } while ((int)((unsigned int)(w >> 32) - want) < 0);
+          reinterpret_cast<float*>(&s_pose[buf][0])[tid] = __uint_as_float((unsigned int)w);
+        }
         __syncthreads();
       }
       // the last warp tries to fetch the NEXT phase's poses while the others are still in this phase
       const int nb = (b + 1 == ps.nblk) ? 0 : b + 1, nit = (b + 1 == ps.nblk) ? it + 1 : it;
       auto hook = [&]() {
         if (warp != PCL_RF_WARPS - 1 || nit == 0 || nit >= ps.num_iter) return;
-        unsigned int ok = 0;
-        if (lane == 0) ok = ((int)(pcl_ld_poll_gpu(ps.ready + nb) - (ps.ready_base[nb] + (unsigned int)nit)) >= 0) ? 1u : 0u;
-        ok = __shfl_sync(0xffffffffu, ok, 0);
-        if (!ok) return;
         const int q0 = nb * ps.npb, nq = min(ps.npb, ps.B - q0);
-        for (int i = lane; i < nq * 12; i += 32) reinterpret_cast<float*>(&s_pose[buf ^ 1][0])[i] = __ldcg(ps.posebuf + (size_t)q0 * 12 + i);
+        const unsigned int want = ps.ready_base[nb] + (unsigned int)nit;
+        unsigned long long w0 = 0ull, w1 = 0ull;                   // <= 48 words: two per lane
+        bool ok = true;
+        if (lane < nq * 12) { w0 = pcl_ld_word_gpu(ps.posebuf + (size_t)q0 * 12 + lane); ok = (int)((unsigned int)(w0 >> 32) - want) >= 0; }
+        if (lane + 32 < nq * 12) { w1 = pcl_ld_word_gpu(ps.posebuf + (size_t)q0 * 12 + lane + 32); ok = ok && (int)((unsigned int)(w1 >> 32) - want) >= 0; }
+        if (!__all_sync(0xffffffffu, ok)) return;                  // not published yet: the phase start will wait for it
+        if (lane < nq * 12) reinterpret_cast<float*>(&s_pose[buf ^ 1][0])[lane] = __uint_as_float((unsigned int)w0);
+        if (lane + 32 < nq * 12) reinterpret_cast<float*>(&s_pose[buf ^ 1][0])[lane + 32] = __uint_as_float((unsigned int)w1);
         if (lane == 0) s_pref[buf ^ 1] = ph + 1;
       };
       const long long c1 = ps.dbg ? clock64() : 0;
