@@ -206,26 +206,28 @@ def test_c1_full_query_matches_reference_run(golden):
     np.testing.assert_allclose(sc.gt_pose, g["gt_pose"])
     xyz, rgb, img = cu(sc.xyz), cu(sc.rgb), cu(sc.img)
     in_t, in_r = make_input(img, xyz, rgb, cfg.num_input, get_init_dict(cfg), cfg.criterion, cfg.num_intermediate)
-    # Start selection: the reference returns the SAME six starts in the same order when run with 8 threads (query_c1.npz)
-    # and with 4 threads (variants.npz: c1_*_t4, tests/golden/make_golden.py variants) — its selection is stable on this
-    # query, so ours must be identical, row by row (no hand-picked 4-of-6 slack).
+    # Start selection: the reference returns the SAME six starts in the same order when run with 8 threads (query_c1.npz),
+    # with 4 and with 2 threads (variants.npz: c1_*_t4 / _t2, tests/golden/make_golden.py variants) — its selection is stable
+    # on this query, so ours must be identical, row by row (no hand-picked 4-of-6 slack).
     v = golden("variants")
-    np.testing.assert_allclose(v["c1_input_trans_t4"], g["input_trans"], atol=1e-6)
-    np.testing.assert_allclose(v["c1_input_rot_t4"], g["input_rot"], atol=1e-6)
+    for tag in ("t4", "t2"):
+        np.testing.assert_allclose(v["c1_input_trans_" + tag], g["input_trans"], atol=1e-6)
+        np.testing.assert_allclose(v["c1_input_rot_" + tag], g["input_rot"], atol=1e-6)
     np.testing.assert_allclose(in_t.cpu().numpy(), g["input_trans"], atol=1e-5)
     np.testing.assert_allclose(in_r.cpu().numpy(), g["input_rot"], atol=1e-5)
     res = omniloc_all(img, xyz, rgb, in_t, in_r, cfg)
     best = int(np.argmin([float(r[2]) for r in res]))
-    assert best == int(g["best"]) == int(v["c1_best_t4"])
+    assert best == int(g["best"]) == int(v["c1_best_t4"]) == int(v["c1_best_t2"])
     t, R = res[best][0].numpy().reshape(3), res[best][1].numpy().astype(np.float64)
-    tr, Rr = g["final_t"][int(g["best"])], g["final_R"][int(g["best"])].astype(np.float64)
-    t4, R4 = v["c1_final_t_t4"][best], v["c1_final_R_t4"][best].astype(np.float64)
+    refs = [(g["final_t"][best].astype(np.float64), g["final_R"][best].astype(np.float64))] + \
+           [(v["c1_final_t_" + tag][best], v["c1_final_R_" + tag][best].astype(np.float64)) for tag in ("t4", "t2")]
     rot = lambda A, B: np.rad2deg(np.arccos(np.clip((np.trace(A.T @ B) - 1) / 2, -1, 1)))
-    # End state: 1 cm / 0.1 deg (north star), widened only to 2 x the distance between the reference's OWN two runs
-    # (Adam amplifies rounding noise: its 8- and 4-thread runs end 2.5 mm / 0.145 deg apart on the winner and up to 1.1 cm
-    # apart on the other candidates; two draws are a thin sample of that jitter, hence the factor 2).  Ours must be that
-    # close to at least one of the two reference runs (measured: 5.5 mm, 0.23 deg).
-    gate_t = max(0.01, 2.0 * np.linalg.norm(tr - t4)); gate_r = max(0.1, 2.0 * rot(Rr, R4))
-    d = min((np.linalg.norm(t - a_), rot(R, B_)) for a_, B_ in ((tr, Rr), (t4, R4)))
-    assert d[0] < gate_t and d[1] < gate_r, (t, tr, t4, d, gate_t, gate_r)
+    # End state: 1 cm / 0.1 deg (north star), widened only to the distance between the reference's OWN runs: Adam amplifies
+    # rounding noise, and its 8-, 4- and 2-thread runs of this very query end up to 8.1 mm / 0.25 deg apart on the winner
+    # (and up to 1.1 cm apart on the other candidates).  Ours must be as close to one of them as they are to each other.
+    spread_t = max(np.linalg.norm(a[0] - b[0]) for a in refs for b in refs)
+    spread_r = max(rot(a[1], b[1]) for a in refs for b in refs)
+    gate_t, gate_r = max(0.01, spread_t), max(0.1, spread_r)
+    d = min(((np.linalg.norm(t - a), rot(R, B)) for a, B in refs), key=lambda x: x[1])
+    assert d[0] < gate_t and d[1] < gate_r, (t, [r[0] for r in refs], d, gate_t, gate_r)
     assert np.linalg.norm(t - sc.gt_pose[:3]) < 0.05
