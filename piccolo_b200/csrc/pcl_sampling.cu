@@ -350,11 +350,13 @@ static PclLaunchPlan pcl_plan(const pcl_cloud* c, int64_t P, bool bwd) {
   if (pb_env > 0 && pb_env <= PCL_MAX_POSE_BLOCK) PB = (int)(pb_env < P ? pb_env : P);
   pl.PB = PB;
   pl.gy = (int)((P + PB - 1) / PB);
-  // 1..4 full waves: take the wave count whose grid fills its slots best (CTAs do equal work)
+  // 1..8 full waves: take the (smallest) wave count whose grid fills its slots best (CTAs do equal work).  Eight, not four:
+  // with 256 pose blocks (P = 8192 forward+backward, 296 slots) every grid of up to 4 waves leaves 13.5 % of the slots empty,
+  // the 7-wave grid 1.2 %
   long long gx = 1;
   double best = -1.0;
   const int w_env = pcl_opt(PCL_OPT_WAVES);
-  for (int w = (w_env > 0 ? w_env : 1); w <= (w_env > 0 ? w_env : 4); ++w) {
+  for (int w = (w_env > 0 ? w_env : 1); w <= (w_env > 0 ? w_env : 8); ++w) {
     long long g = (long long)resident * w / pl.gy;
     if (g < 1) g = 1;
     if (g > pl.n_rows) g = pl.n_rows;
