@@ -20,6 +20,9 @@
 #include <string.h>
 
 #define PCL_GRID_MAX_ROT 32
+#ifndef PCL_GRID_MAX_WAVES
+#define PCL_GRID_MAX_WAVES 4
+#endif
 #define PCL_GRID_TOL 1e-6       // third rows closer than this (fp64 from the fp32 angles) are the same group
 
 struct PclGridPlan {
@@ -293,7 +296,7 @@ extern "C" int pcl_score_grid(const pcl_cloud* c, const pcl_image* im, const flo
   const int resident = pcl_num_sms() * 3;
   long long gx = 1;
   double best = -1.0;
-  for (int w = 1; w <= 4; ++w) {                          // 1..4 whole resident waves, the best-filled one
+  for (int w = 1; w <= PCL_GRID_MAX_WAVES; ++w) {         // whole resident waves, the best-filled count
     long long g = (long long)resident * w / gy;
     if (g < 1) g = 1;
     if (g > n_rows) g = n_rows;
