@@ -95,17 +95,18 @@ def localize_query(cloud: engine.Cloud, image: engine.Image, grid: torch.Tensor,
 
 def localize_query_host(xyz_h: torch.Tensor, rgb_h: torch.Tensor, img_h: torch.Tensor, grid_h, cfg, device):
     """End-to-end call with HOST (pinned) buffers: upload, pack, score, refine, and read the answer back.
+    `rgb_h` / `img_h` may be float32 in [0,1] (the reference's tensors) or uint8 (its data before `/ 255.`).
     Returns (pose (6,) cpu, loss cpu float).  The panorama travels on the upload stream while the cloud is packed
     (Morton sort, clamp box) on the current one; the two join before scoring."""
     main, side = torch.cuda.current_stream(device), _side_stream(device)
     xyz = xyz_h.to(device, non_blocking=True)
-    rgb = rgb_h.to(device, non_blocking=True)
+    rgb = _unit_from_host(rgb_h, device)                 # float32, or uint8 (expanded to k/255 on the device)
     grid = grid_h.to(device, non_blocking=True)          # (P,6) tensor or StartGrid
     copied = main.record_event()
     cloud = engine.Cloud(xyz, rgb, cfg.out_of_room_quantile)      # enqueued first: Image() below waits on the host for one word
     side.wait_event(copied)                              # copies share the link: the panorama queues behind the cloud's arrays
     with torch.cuda.stream(side):
-        img = img_h.to(device, non_blocking=True)
+        img = _unit_from_host(img_h, device)
         img.record_stream(main)
         image = engine.Image(img)
     main.wait_stream(side)
@@ -115,6 +116,21 @@ def localize_query_host(xyz_h: torch.Tensor, rgb_h: torch.Tensor, img_h: torch.T
 
 
 _SIDE_STREAMS = {}
+_U8_TABLES = {}
+
+
+def _unit_from_host(t_h: torch.Tensor, device) -> torch.Tensor:
+    """Host buffer -> float32 device tensor.  float32 buffers are uploaded as they are; uint8 buffers (what the reference's
+    loaders hold before their `/ 255.`: cv2 images, integer colour columns) are uploaded as bytes — a quarter of the PCIe
+    traffic — and expanded on the device through a 256-entry table of the correctly rounded k/255 (torch's CUDA division by a
+    scalar multiplies by the reciprocal and would not give the values the reference computes on the host)."""
+    if t_h.dtype != torch.uint8:
+        return t_h.to(device, non_blocking=True)
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _U8_TABLES:
+        _U8_TABLES[key] = (torch.arange(256, dtype=torch.float32) / 255.).to(device)
+    return _U8_TABLES[key][t_h.to(device, non_blocking=True).long()]
+
 
 
 def _side_stream(device) -> "torch.cuda.Stream":
@@ -138,9 +154,9 @@ def localize_stream(queries, cfg, device, num_split=(4, 4)):
         xyz_h, rgb_h, img_h, grid_h = q
         with torch.cuda.stream(side):
             xyz = xyz_h.to(device, non_blocking=True)
-            rgb = rgb_h.to(device, non_blocking=True)
+            rgb = _unit_from_host(rgb_h, device)
             cloud = engine.Cloud(xyz, rgb, cfg.out_of_room_quantile)
-            img = img_h.to(device, non_blocking=True)
+            img = _unit_from_host(img_h, device)
             grid = grid_h.to(device, non_blocking=True)
             image = engine.Image(img)
             ready = torch.cuda.Event()
